@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- the terrain hot path at BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--division D] [--octaves O] [--iters I]
+
+Workload (BASELINE.json configs[3]): division-2500 icosphere (62 500 002 vertices), 8-octave
+OpenSimplex fBm at every vertex, height assembly (nixis.py:332-364), then 1000 erosion sweeps
+(erosion_iteration3).  One "step" = one such pass over the whole planet.
+
+Metric: BASELINE.json names two throughputs -- Mvert*octaves/s (fBm) and Mvert-iterations/s
+(erosion).  A step performs V*(octaves+iterations) "vertex-passes" (one octave evaluated, or one
+erosion sweep applied, at one vertex); `value` is vertex-passes per second over the whole step,
+in millions, and the two component throughputs with their own rooflines are reported in the
+`fbm` and `erosion` objects of the same JSON line.
+
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_VERT_OCT = 152.4      # as-written FP ops of noise3d + the fBm wrapper
+BYTES_PER_VERT_ITER = 60.0     # erosion_iteration3, FP32 state + int32 ELL + float xyz
+METRIC = "Mvert*(octaves+iterations)/s: fBm Mvert*octaves/s and erosion Mvert-iters/s at d=2500"
+UNIT = "Mvert-passes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--division", type=int, default=2500)
+    ap.add_argument("--octaves", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_reference_sample(octaves, iters, budget_s=20.0, division=320, seed=12345):
+    """The reference's CPU algorithm (oracle restatement, OpenMP over all host cores) on a bounded
+    sample of the same workload: a division-`division` icosphere, same octaves, as many erosion
+    sweeps as fit the time budget.  Returns the component rates and the composed whole-step rate
+    for the octaves:iterations mix of the real workload."""
+    from oracle import oracle, icosphere
+    import numpy as np
+    oracle.build()
+    cores = oracle.num_threads()
+    pts, cells = icosphere.icosa_sphere(division)
+    V = len(pts)
+    perm, pgi = oracle.init(seed)
+    adj = oracle.build_adjacency(cells)
+    oracle.sort_adjacency(adj)
+    oracle.sample_octaves(pts[:10000], None, perm, pgi, 1)          # warm the thread pool
+    t0 = time.perf_counter()
+    h = oracle.sample_octaves(pts, None, perm, pgi, octaves, 1.5, 0.4, 2.5, 0.5, 1.0)
+    t_fbm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    h, _, _ = oracle.height_assembly(h)
+    t_asm = time.perf_counter() - t0
+    wat, sed = np.zeros_like(h), np.zeros_like(h)
+    wat += 0.3 / 320
+    t0 = time.perf_counter()
+    oracle.erosion_iteration3(pts, adj, h, wat, sed)
+    t_one = time.perf_counter() - t0
+    n_it = int(max(3, min(iters, (budget_s - t_fbm - t_asm) / max(t_one, 1e-6))))
+    t0 = time.perf_counter()
+    oracle.erode_terrain3(pts, adj, h, n_it)
+    t_ero = time.perf_counter() - t0
+    fbm_rate = V * octaves / t_fbm / 1e6
+    ero_rate = V * n_it / t_ero / 1e6
+    t_full = t_fbm + t_asm + iters * (t_ero / n_it)
+    value = V * (octaves + iters) / t_full / 1e6
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "fbm_mvert_oct_s": fbm_rate, "erosion_mvert_iter_s": ero_rate,
+            "sample": f"oracle (C restatement of the reference, OpenMP x{cores}) on a d={division} icosphere "
+                      f"({V} verts): {octaves} octaves in {t_fbm:.3f}s, assembly {t_asm:.3f}s, {n_it} erosion sweeps "
+                      f"in {t_ero:.3f}s; whole-step rate composed for the {octaves}:{iters} octave:sweep mix"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (its algorithm restated in
+    oracle/, the reference itself is Python/numba and /root/reference does not exist on the GPU box),
+    all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, infos = [], []
+    for i in range(args.warmup + args.steps):
+        info = cpu_reference_sample(args.octaves, args.iters, budget_s=12.0)
+        if i >= args.warmup:
+            vals.append(info["value"]); infos.append(info)
+    v = statistics.mean(vals)
+    V = 10 * args.division ** 2 + 2
+    info = infos[-1]
+    info["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": V * (args.octaves + args.iters) / (v * 1e6) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "cpu_baseline": info,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "ms_per_step is the d=2500 step time extrapolated from the bounded sample"}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"icosphere d={args.division} ({10 * args.division ** 2 + 2} verts), {args.octaves}-octave "
+                        f"OpenSimplex fBm + height assembly + {args.iters} erosion_iteration3 sweeps, seed {args.seed}, R=1",
+            "division": args.division, "octaves": args.octaves, "erosion_iters": args.iters,
+            "l2": "inputs larger than L2 (state 3x250 MB + adjacency 1.5 GB + xyz 1 GB per sweep)",
+            "parallelism": f"vertex-range shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nixis_b200 import _lib, runtime as rt
+    from nixis_b200 import terrain, util, erosion, opensimplex
+    from nixis_b200.pipeline import TerrainPipeline, assemble_heights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if world > 1:
+        from nixis_b200.multigpu import run_multi_gpu_bench
+        return run_multi_gpu_bench(args, rank, world, local)
+
+    k, n_oct, iters = args.division, args.octaves, args.iters
+    pipe = TerrainPipeline(k, seed=args.seed, n_octaves=n_oct, radius=1.0)
+    pipe.build_mesh()
+    V = pipe.V
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    h_buf = torch.empty(V, dtype=torch.float32, device=pipe.device)
+    state = {}
+
+    def step(timed=None):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        mm = rt.new_minmax(pipe.device)
+        h = pipe.fbm(out=h_buf, minmax=mm)
+        e[1].record()
+        h, _, _ = assemble_heights(h, mm=mm)
+        e[2].record()
+        st = pipe.erosion_state(h)
+        st.run(iters)
+        e[3].record()
+        state["st"] = st
+        if timed is not None:
+            timed.append(e)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count
+    timed = []
+    t_start, t_end = ev(), ev()
+    torch.cuda.synchronize()
+    t_start.record()
+    for _ in range(args.steps):
+        step(timed)
+    t_end.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = _lib.launch_count - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    ms_per_step = total_ms / args.steps
+    fbm_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in timed)
+    asm_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in timed)
+    ero_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in timed)
+    value = V * (n_oct + iters) / (ms_per_step * 1e-3) / 1e6
+
+    # non-finite bookkeeping: erosion_iteration3 diverges by construction
+    hfin = state["st"].heights
+    nonfinite = int((~torch.isfinite(hfin)).sum().item())
+
+    hbm_peak, hbm_src = measured_peaks()
+    fp32_peak = rt.ffma_peak_tflops()
+    ero_launch_ms = ero_ms / iters
+    ero_gbs = BYTES_PER_VERT_ITER * V / (ero_launch_ms * 1e-3) / 1e9
+    fbm_tflops = FLOP_PER_VERT_OCT * V * n_oct / (fbm_ms * 1e-3) / 1e12
+    roofline = {"kernel": "erode3_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ero_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_VERT_ITER * V, "avg_launch_ms": ero_launch_ms}
+    fbm_obj = {"value": V * n_oct / (fbm_ms * 1e-3) / 1e6, "unit": "Mvert*octaves/s", "ms": fbm_ms,
+               "roofline": {"kernel": "fbm_kernel<3>", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
+                            "unit": "TFLOP/s", "frac": fbm_tflops / fp32_peak,
+                            "peak_source": "measured here: nxb_ffma_peak FFMA microbenchmark",
+                            "algorithmic_flop_per_vert_octave": FLOP_PER_VERT_OCT}}
+    ero_obj = {"value": V * iters / (ero_ms * 1e-3) / 1e6, "unit": "Mvert-iters/s", "ms": ero_ms,
+               "nonfinite_heights_after_last_step": nonfinite}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "fbm": fbm_obj, "assembly_ms": asm_ms, "erosion": ero_obj, "roofline": roofline,
+            "clocks": clocks, "gpu_launches": launches}
+
+    # ---- end to end through the reference-named API with HOST (pinned) buffers -------------
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(args, pipe, np, torch, rt, terrain, util, erosion)
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_reference_sample(n_oct, iters)
+    print(json.dumps(line))
+
+
+def pinned(np, torch, shape, dtype):
+    t = torch.empty(shape, dtype=dtype, pin_memory=True)
+    return t.numpy()
+
+
+def run_e2e(args, pipe, np, torch, rt, terrain, util, erosion):
+    """Same step through the functions nixis.py would call, numpy in / numpy out: every call copies
+    its inputs host->device and its result device->host inside the timed region."""
+    k, n_oct, iters = args.division, args.octaves, args.iters
+    V = pipe.V
+    # host inputs, as nixis.py holds them: points f64 [V,3], neighbors int32 [V,6]
+    points = pinned(np, torch, (V, 3), torch.float64)
+    torch.from_numpy(points).copy_(rt.mesh_points(k, f32=False, f64=True)[1])
+    neighbors = pinned(np, torch, (V, 6), torch.int32)
+    torch.from_numpy(neighbors).copy_(pipe.adj)
+    perm, pgi = pipe.perm, pipe.pgi
+    torch.cuda.synchronize()
+    h2d = d2h = 0
+
+    def one():
+        nonlocal h2d, d2h
+        h = terrain.sample_octaves(points, None, perm, pgi, n_oct, 1.5, 0.4, 2.5, 0.5, 1.0, verbose=False)   # nixis.py:330
+        h2d_ = points.nbytes; d2h_ = h.nbytes
+        h = util.rescale(h, -4000, 8850)
+        h2d_ += h.nbytes; d2h_ += h.nbytes
+        minval, maxval = np.amin(h), np.amax(h)
+        level = util.find_percent_val(minval, maxval, 55.0)
+        ocean = terrain.make_bool_elevation_mask(h, level)
+        h2d_ += h.nbytes; d2h_ += ocean.nbytes
+        h = util.power_rescale(h, mask=ocean, mode=1, power=0.5, verbose=False)
+        h = util.power_rescale(h, mask=ocean, mode=0, power=2.0, verbose=False)
+        h2d_ += 2 * (h.nbytes + ocean.nbytes); d2h_ += 2 * h.nbytes
+        h -= level
+        h = util.rescale(h, -4000, 8850, mid=0)
+        h2d_ += h.nbytes; d2h_ += h.nbytes
+        erosion.erode_terrain3(points, neighbors, h, num_iter=iters, verbose=False)
+        h2d_ += points.nbytes + neighbors.nbytes + h.nbytes; d2h_ += h.nbytes
+        h2d, d2h = h2d_, d2h_
+        return h
+
+    one()                                   # warm-up
+    torch.cuda.synchronize()
+    reps = max(1, min(2, args.steps))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": V * (n_oct + iters) / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "nixis_b200.terrain.sample_octaves / util.rescale / power_rescale / erosion.erode_terrain3 "
+                   "with float64 numpy arrays (points / neighbours pinned, intermediate heights pageable as numpy returns them)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

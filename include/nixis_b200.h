@@ -1,0 +1,151 @@
+/*
+ * nixis_b200.h -- C-ABI of libnixis_b200.so (hand-written sm_100a CUDA).
+ *
+ * The reference (MightyBOBcnc/nixis) has no FFI layer: its hot path is plain
+ * Python functions that nixis.py imports by name.  This header is therefore the
+ * boundary a maintainer binds with ctypes (INTEGRATION.md shows the stub); every
+ * entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - Pointers are DEVICE pointers unless the name ends in _h / _host.
+ *  - Every function returns 0 on success or a negative nxb_status; it never
+ *    throws.  nxb_last_error() returns the text of the last failure (thread-local).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous on that stream unless stated otherwise.
+ *  - Thread-compatible, not thread-safe per handle.
+ *  - Device state is FP32 (heights, water, sediment, unit-sphere positions);
+ *    integer tables (perm, cells, adjacency) are bit-exact w.r.t. the reference.
+ */
+#ifndef NIXIS_B200_H
+#define NIXIS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NXB_ABI_VERSION 1
+
+typedef enum {
+    NXB_OK = 0,
+    NXB_ERR_CUDA = -1,        /* a CUDA runtime call failed (see nxb_last_error) */
+    NXB_ERR_ARG = -2,         /* bad argument */
+    NXB_ERR_OVERFLOW = -3,    /* adjacency row overflow (inconsistent winding) */
+    NXB_ERR_UNSUPPORTED = -4
+} nxb_status;
+
+/* positions on the device: unit-sphere xyz in .x .y .z, .w unused (16-byte loads) */
+typedef struct { float x, y, z, w; } nxb_float4;
+
+/* ---- library ----------------------------------------------------------- */
+int nxb_version(void);
+int nxb_last_error(char *buf, int len);
+/* sm count, clock (kHz), total memory of the CURRENT device */
+int nxb_device_info(int *sm_count, int *sm_clock_khz, int64_t *mem_bytes, int *cc_major, int *cc_minor);
+/* FP32 FFMA microbenchmark on the current device: dependent-free FFMA chains on
+ * every SM; returns achieved TFLOP/s (FMA = 2 flops).  Synchronous.  Used as the
+ * measured FP32 roofline denominator (MEASURED_PEAKS.json has no FP32 entry). */
+int nxb_ffma_peak(int iters, double *tflops_out);
+
+/* ---- opensimplex.py ---------------------------------------------------- */
+/* opensimplex.py:90-112 init(seed) incl. the int32 truncation of `over`.  HOST. */
+int nxb_init_perm(int64_t seed, int32_t *perm_host, int32_t *pgi_host);
+/* Pack perm / perm_grad_index_3D into the device lookup tables the kernels stage
+ * in shared memory.  Synchronous (tiny H2D).  handle_out receives an opaque pointer. */
+int nxb_tables_create(const int32_t *perm_host, const int32_t *pgi_host, void **handle_out);
+int nxb_tables_destroy(void *handle);
+/* opensimplex.py:257-263 noisearr3d / :144-150 noisearr2d / :762-768 noisearr4d:
+ * one evaluation per element, FP32 in/out. */
+int nxb_noise3_f32(void *tables, const float *x, const float *y, const float *z, int64_t n, float *out, void *stream);
+int nxb_noise2_f32(void *tables, const float *x, const float *y, int64_t n, float *out, void *stream);
+int nxb_noise4_f32(void *tables, const float *x, const float *y, const float *z, const float *w, int64_t n, float *out, void *stream);
+
+/* ---- terrain.py -------------------------------------------------------- */
+/* terrain.py:12-59 sample_noise + sample_octaves fused over all octaves:
+ *   out[v] = (init ? init[v] : 0) + sum_o ((noise3(xyz[v]*freq[o]) + 1) * 0.5) * amp[o]
+ * freq_host/amp_host: n_oct doubles each, already advanced octave by octave the way
+ * terrain.py:44-45 does (freq *= roughness; amp *= persistence), in UNIT-sphere units
+ * (the reference's n_freq/world_radius applied to radius-scaled verts is the same number).
+ * minmax (nullable, device float[2]) receives min/max of out over [0,n) merged into its
+ * current content (initialise with +inf/-inf), for terrain.py:50-53 and util.rescale. */
+int nxb_fbm3_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
+                 const double *freq_host, const double *amp_host,
+                 const float *init, float *out, float *minmax, void *stream);
+/* 4-D variant (no reference driver exists; w coordinate = w_host[o] per octave). */
+int nxb_fbm4_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
+                 const double *freq_host, const double *amp_host, const double *w_host,
+                 const float *init, float *out, float *minmax, void *stream);
+/* terrain.py:61-72 make_bool_elevation_mask */
+int nxb_mask_le_f32(const float *h, int64_t n, float level, uint8_t *mask, void *stream);
+
+/* ---- util.py: mesh ------------------------------------------------------ */
+/* util.py:17-50 create_mesh -> meshzoo.icosa_sphere(k) (layout: SURVEY App. B,
+ * parity unpinned).  Vertices [v_begin, v_end) of the k-division icosphere, closed form.
+ * xyz_f32 and/or xyz_f64 (double[.][3]) may be NULL. */
+int nxb_mesh_icosa_points(int k, int64_t v_begin, int64_t v_end, nxb_float4 *xyz_f32, double *xyz_f64, void *stream);
+/* triangles [t_begin, t_end) as int32[.][3] */
+int nxb_mesh_icosa_cells(int k, int64_t t_begin, int64_t t_end, int32_t *cells, void *stream);
+/* double[n][3] * scale -> float4 (used to ingest caller-supplied float64 vertices) */
+int nxb_xyz_f64_to_f32(const double *xyz_f64, int64_t n, double scale, nxb_float4 *xyz_f32, void *stream);
+
+/* ---- util.py: adjacency -------------------------------------------------- */
+/* util.py:591-613 build_adjacency.  cells int32[T][3]; adj int32[V][6], -1 padded.
+ * workspace: device scratch of nxb_adj_build_workspace(V) bytes.  Deterministic
+ * (slot = rank of the triangle index among the triangles around the vertex).
+ * Synchronous at the end (reads back the overflow flag). */
+int64_t nxb_adj_build_workspace(int64_t V);
+int nxb_adj_build(const int32_t *cells, int64_t T, int64_t V, int32_t *adj, void *workspace, void *stream);
+/* util.py:623-662 sort_adjacency, race-free: reads adj_in, writes adj_out (must differ). */
+int nxb_adj_sort(const int32_t *adj_in, int32_t *adj_out, int64_t V, void *stream);
+
+/* ---- util.py: rescale ---------------------------------------------------- */
+/* min/max of x merged into minmax[2] (device; initialise with +inf/-inf via nxb_minmax_reset) */
+int nxb_minmax_reset(float *minmax, void *stream);
+int nxb_minmax_f32(const float *x, int64_t n, float *minmax, void *stream);
+/* util.py:110-175 rescale.  x_min/x_max are passed by the caller (after the u_min/u_max
+ * widening and, multi-GPU, the all-reduce).  mode: 0 None, 1 'lower', 2 'upper'.
+ * out may alias x. */
+int nxb_rescale_f32(const float *x, int64_t n, float x_min, float x_max, float lower, float upper,
+                    int has_mid, float mid, int mode, float *out, void *stream);
+/* util.py:178-254 power_rescale, pass 1: statistics of the selected elements
+ * (sel_mode 1 -> mask true, 0 -> mask false) in ONE ordered pass.  summary4 (device float[4])
+ * receives (has, F, U, M): has = 1 if anything is selected, F = first selected value,
+ * M = min selected, U = max over selected values that are >= the min of the selected values
+ * before them.  The reference's sequential if/elif scan (util.py:203-214) is then
+ *     mask_lower = min(x_max, M);  mask_upper = max(x_min, U, F >= x_max ? F : -inf)
+ * Shards combine in index order: F = first shard's F, M = min, U = max(U_a, U_b, F_b >= M_a ? F_b : -inf). */
+int nxb_power_summary_f32(const float *x, const uint8_t *mask, int64_t n, int sel_mode,
+                          float *summary4, void *stream);
+/* Pass 2: out = selected ? pow((x-lo)/(hi-lo), power)*(hi-lo)+lo : x.  out may alias x.
+ * sel_mode -1 = mode None (nothing selected).
+ * `shift` is subtracted from every element afterwards (nixis.py:359 `height -= ocean_level`
+ * fused; pass 0 otherwise). */
+int nxb_power_apply_f32(const float *x, const uint8_t *mask, int64_t n, int sel_mode,
+                        float lo, float hi, float power, float shift, float *out, void *stream);
+
+/* ---- erosion.py ---------------------------------------------------------- */
+/* erosion.py:197-279 erosion_iteration3 for vertices [v_begin, v_end), FP32 state,
+ * ping-pong buffers (reads *_in, writes *_out; no copy-back pass).  `rain` is added to
+ * every water value read (erosion.py:182-183 `water += rain_amount` fused).  `radius`
+ * scales unit-sphere distances (nodes are radius-scaled in the reference). */
+int nxb_erode3_step_f32(const nxb_float4 *xyz_unit, const int32_t *adj,
+                        const float *h_in, const float *w_in, const float *s_in,
+                        float *h_out, float *w_out, float *s_out,
+                        int64_t v_begin, int64_t v_end, float rain, float radius, void *stream);
+/* erosion.py:76-99 erosion_iteration1 */
+int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
+                        int64_t v_begin, int64_t v_end, void *stream);
+/* gather / scatter of halo values for the multi-GPU exchange: dst[i] = src[idx[i]] and
+ * dst[idx[i]] = src[i] */
+int nxb_gather_f32(const float *src, const int32_t *idx, int64_t n, float *dst, void *stream);
+int nxb_scatter_f32(const float *src, const int32_t *idx, int64_t n, float *dst, void *stream);
+
+/* float <-> double conversion of result arrays (reference API is float64) */
+int nxb_f32_to_f64(const float *src, int64_t n, double *dst, void *stream);
+int nxb_f64_to_f32(const double *src, int64_t n, float *dst, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

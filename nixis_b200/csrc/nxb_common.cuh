@@ -1,0 +1,96 @@
+// Shared helpers for libnixis_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/nixis_b200.h"
+
+#define NXB_API extern "C" __attribute__((visibility("default")))
+
+void nxb_set_error(const char *fmt, ...);
+
+#define NXB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            nxb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,              \
+                          cudaGetErrorString(e__));                                 \
+            return NXB_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define NXB_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            nxb_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__,          \
+                          cudaGetErrorString(e__));                                 \
+            return NXB_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define NXB_ARG(cond)                                                               \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            nxb_set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond);     \
+            return NXB_ERR_ARG;                                                     \
+        }                                                                           \
+    } while (0)
+
+// B200: 148 SMs.  Grids for streaming kernels are sized in whole waves.
+int nxb_sm_count();
+
+static inline int nxb_grid_for(int64_t n, int block, int max_ctas_per_sm)
+{
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)nxb_sm_count() * max_ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// float atomic min/max through the ordered-int trick (works for all finite + inf)
+__device__ __forceinline__ void atomic_min_f32(float *addr, float v)
+{
+    v += 0.0f;  // -0.0 -> +0.0 (its int image would be INT_MIN)
+    if (v >= 0.0f) atomicMin((int *)addr, __float_as_int(v));
+    else atomicMax((unsigned int *)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v)
+{
+    v += 0.0f;
+    if (v >= 0.0f) atomicMax((int *)addr, __float_as_int(v));
+    else atomicMin((unsigned int *)addr, __float_as_uint(v));
+}
+
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide min/max merged into gmem minmax[2] with one atomic pair per block.
+// NaNs are ignored by fminf/fmaxf, like np.min would NOT -- callers that need NaN
+// propagation check finiteness separately (erosion divergence counter).
+__device__ __forceinline__ void block_minmax_commit(float lo, float hi, float *minmax)
+{
+    __shared__ float s_lo[32], s_hi[32];
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_lo[w] = lo; s_hi[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+        lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+        hi = lane < nw ? s_hi[lane] : __int_as_float(0xff800000);
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lane == 0) { atomic_min_f32(minmax, lo); atomic_max_f32(minmax + 1, hi); }
+    }
+}

@@ -1,0 +1,115 @@
+"""Device-resident driver of the terrain hot path (nixis.py:247-417 call order) for 1..N GPUs.
+
+    mesh (closed form, on device) -> adjacency (build + ring sort) -> fBm (all octaves fused)
+    -> height assembly (nixis.py:332-364) -> erosion sweeps (erosion.py:172-279)
+
+Single GPU: everything stays in HBM, the host only sees a few scalars (min/max, ocean level).
+Multi GPU (one process per GPU, torch.distributed): the vertex index range is split into
+contiguous shards (see partition.py); fBm and the elementwise passes need no communication,
+the min/max / power_rescale statistics need a few scalars all-gathered, and erosion exchanges
+the boundary heights / water once per sweep (halo.py).
+"""
+import numpy as np
+import torch
+
+from . import runtime as rt
+from .util import DeviceMesh
+
+# nixis.py:312-320
+MIN_ALT, MAX_ALT, OCEAN_PERCENT = -4000.0, 8850.0, 55.0
+N_INIT_ROUGH, N_INIT_STRENGTH, N_ROUGHNESS, N_PERSISTENCE = 1.5, 0.4, 2.5, 0.5
+
+
+def find_percent_val(minval, maxval, percent):
+    return minval + ((maxval - minval) * percent / 100.0)      # util.py:556-566
+
+
+class Collective:
+    """The handful of scalar exchanges the sharded assembly needs.  world=1: identity."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+
+    def minmax(self, mm):
+        """mm: float32[2] CUDA tensor (local min, max) -> global (min, max) host floats."""
+        if self.dist and self.world > 1:
+            lo = mm[0:1].clone()
+            hi = mm[1:2].clone()
+            self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
+            self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
+            return float(lo.item()), float(hi.item())
+        lo, hi = mm.tolist()
+        return lo, hi
+
+    def gather_summaries(self, s):
+        """s: float32[4] CUDA tensor -> list of per-rank (has, F, U, M) host tuples, rank order."""
+        if self.dist and self.world > 1:
+            buf = [torch.empty_like(s) for _ in range(self.world)]
+            self.dist.all_gather(buf, s, group=self.group)
+            return [b.tolist() for b in buf]
+        return [s.tolist()]
+
+
+def assemble_heights(h, coll=None, min_alt=MIN_ALT, max_alt=MAX_ALT, ocean_percent=OCEAN_PERCENT, mm=None):
+    """nixis.py:332-364 on a (shard of a) float32 CUDA height vector, in place where possible.
+    Returns (height, ocean mask uint8, ocean_level)."""
+    coll = coll or Collective()
+    lo, hi = coll.minmax(mm if mm is not None else rt.minmax(h))
+    h = rt.rescale(h, lo, hi, min_alt, max_alt, out=h)                       # nixis.py:332
+    minval, maxval = coll.minmax(rt.minmax(h))                                # :337-338
+    ocean_level = find_percent_val(minval, maxval, ocean_percent)             # :343
+    ocean = rt.mask_le(h, ocean_level)                                        # :346
+    for mode, power, shift in ((1, 0.5, 0.0), (0, 2.0, ocean_level)):         # :352-359
+        x_min, x_max = (minval, maxval) if mode == 1 else coll.minmax(rt.minmax(h))
+        summ = rt.combine_power_summaries(coll.gather_summaries(rt.power_summary(h, ocean, mode)))
+        p_lo, p_hi = rt.power_bounds(summ, x_min, x_max)
+        h = rt.power_apply(h, ocean, mode, p_lo, p_hi, power, shift, out=h)
+    lo, hi = coll.minmax(rt.minmax(h))
+    h = rt.rescale(h, lo, hi, min_alt, max_alt, mid=0.0, out=h)               # :361
+    return h, ocean, ocean_level
+
+
+class TerrainPipeline:
+    """One GPU's share of the planet.  world=1 -> the whole planet."""
+
+    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, rank=0, world=1, device=None):
+        rt.require_cuda()
+        self.k, self.seed, self.n_octaves, self.radius = int(k), seed, int(n_octaves), float(radius)
+        self.rank, self.world = rank, world
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.V = 10 * self.k ** 2 + 2
+        self.T = 20 * self.k ** 2
+        self.perm, self.pgi = rt.init_perm(seed)
+        self.tables = rt.tables_for(self.perm, self.pgi)
+        self.freq, self.amp = rt.octave_schedule(n_octaves, N_INIT_ROUGH, N_INIT_STRENGTH, N_ROUGHNESS, N_PERSISTENCE)
+        self.mesh = None
+        self.adj = None
+
+    # ---- single-GPU stages -------------------------------------------------------
+    def build_mesh(self, with_adjacency=True):
+        xyz, _ = rt.mesh_points(self.k, device=self.device)
+        self.mesh = DeviceMesh(self.k, xyz, self.radius)
+        if with_adjacency:
+            cells = rt.mesh_cells(self.k, device=self.device)
+            unsorted = rt.adj_build(cells, self.V)
+            del cells
+            self.adj = rt.adj_sort(unsorted)
+            del unsorted
+            self.mesh.adj = self.adj
+        return self.mesh
+
+    def fbm(self, out=None, minmax=None):
+        return rt.fbm3(self.tables, self.mesh.xyz, self.freq, self.amp, out=out, minmax=minmax)
+
+    def heights(self):
+        mm = rt.new_minmax(self.device)
+        h = self.fbm(minmax=mm)
+        return assemble_heights(h, mm=mm)
+
+    def erosion_state(self, heights32):
+        from .erosion import Erosion3State
+        return Erosion3State(self.mesh.xyz, self.radius, self.adj, heights32)

@@ -1,0 +1,89 @@
+"""Drop-in for the reference's `terrain` module (terrain.py) on B200.
+
+`sample_octaves` keeps the reference signature and semantics (terrain.py:32-59): octave o
+uses frequency f0*roughness^o and amplitude a0*persistence^o (advanced in float64 on the
+host), each octave adds ((noise3d+1)*0.5)*amplitude, `elevations` is accumulated in place
+when given, and the same progress lines are printed when `verbose`.  All octaves run in ONE
+fused kernel (nxb_fbm3_f32) instead of one numba prange per octave.
+
+Inputs may be numpy (float64, radius-scaled vertices like nixis.py:249 -- copied to the GPU,
+result returned as float64 numpy) or a `util.DeviceMesh` / CUDA tensors (resident fast path,
+CUDA float32 tensor returned).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import runtime as rt
+from .util import DeviceMesh, _device_xyz
+
+
+def sample_noise(verts, perm, pgi, n_roughness=1, n_strength=0.2, radius=1):
+    """One octave (terrain.py:12-29): ((noise3d(verts*n_roughness)+1)*0.5)*n_strength*radius."""
+    xyz, fscale = _device_xyz(verts, 1.0)
+    tables = rt.tables_for(perm, pgi)
+    out = rt.fbm3(tables, xyz, [float(n_roughness) * fscale], [float(n_strength) * float(radius)])
+    return out if _is_device(verts) else rt.download_f64(out)
+
+
+def _is_device(v):
+    return isinstance(v, (DeviceMesh, torch.Tensor))
+
+
+def sample_octaves(verts, elevations, perm, pgi, n_octaves=1, n_init_roughness=1.5, n_init_strength=0.4,
+                   n_roughness=2.0, n_persistence=0.5, world_radius=1.0, verbose=True, minmax=None):
+    """Sample octaves of noise and combine them together (terrain.py:32-59)."""
+    t0 = time.perf_counter()
+    # the kernel works on unit-sphere float positions; nr = freq/world_radius applied to the
+    # radius-scaled verts (terrain.py:17,43) is the same lattice coordinate
+    xyz, fscale = _device_xyz(verts, 1.0 / float(world_radius))
+    tables = rt.tables_for(perm, pgi)
+    freq, amp = rt.octave_schedule(n_octaves, n_init_roughness, n_init_strength, n_roughness, n_persistence)
+    freq = [f * fscale for f in freq]
+    device_io = _is_device(verts)
+    init = None
+    if elevations is not None:
+        init = elevations if isinstance(elevations, torch.Tensor) else rt.upload_f32(elevations)
+    mm = minmax if minmax is not None else rt.new_minmax(xyz.device)
+    out = rt.fbm3(tables, xyz, freq, amp, init=init,
+                  out=init if isinstance(elevations, torch.Tensor) else None, minmax=mm)
+    if verbose:
+        torch.cuda.synchronize()
+        print(f"  Octaves 1..{n_octaves} (fused): {time.perf_counter() - t0:.5f} sec")
+        lo, hi = mm.tolist()
+        print("  Combined octaves min:", lo)
+        print("  Combined octaves max:", hi)
+    if device_io or isinstance(elevations, torch.Tensor):
+        return out
+    if elevations is not None:               # in place, like `elevations +=` (terrain.py:43)
+        return rt.download_f64(out, out=elevations)
+    return rt.download_f64(out)
+
+
+def sample_octaves4(verts, elevations, perm, n_octaves=1, n_init_roughness=1.5, n_init_strength=0.4,
+                    n_roughness=2.0, n_persistence=0.5, world_radius=1.0, w_scale=0.5, verbose=False):
+    """4-D fBm.  NOT a reference function (nothing in nixis calls noise4d): defined
+    by analogy with sample_octaves, the 4th coordinate of octave o is w_scale * freq_o."""
+    xyz, fscale = _device_xyz(verts, 1.0 / float(world_radius))
+    tables = rt.tables_for(perm, None)
+    freq, amp = rt.octave_schedule(n_octaves, n_init_roughness, n_init_strength, n_roughness, n_persistence)
+    w = [w_scale * f for f in freq]
+    freq = [f * fscale for f in freq]
+    init = None
+    if elevations is not None:
+        init = elevations if isinstance(elevations, torch.Tensor) else rt.upload_f32(elevations)
+    out = rt.fbm4(tables, xyz, freq, amp, w, init=init)
+    if _is_device(verts) or isinstance(elevations, torch.Tensor):
+        return out
+    if elevations is not None:
+        return rt.download_f64(out, out=elevations)
+    return rt.download_f64(out)
+
+
+def make_bool_elevation_mask(height, mask_elevation):
+    """mask[h] = height[h] <= mask_elevation (terrain.py:61-72)."""
+    if isinstance(height, torch.Tensor):
+        return rt.mask_le(height, float(mask_elevation))
+    h = rt.upload_f32(height)
+    return rt.mask_le(h, float(mask_elevation)).cpu().numpy().view(np.bool_)

@@ -1,0 +1,163 @@
+"""Drop-in for the hot-path half of the reference's `util` module (util.py) on B200.
+
+Kept: `create_mesh`, `rescale`, `power_rescale`, `find_percent_val`, `build_adjacency`,
+`sort_adjacency` -- same names, argument order, defaults, return / in-place conventions.
+Everything else in the reference's util.py (image export, KD-tree, file I/O, lat/lon) is
+outside the hot path and is not provided here.
+
+numpy in -> numpy out (float64 / int32, like the reference); `DeviceMesh` and CUDA tensors
+in -> CUDA tensors out (the resident path bench.py and the multi-GPU driver use).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import runtime as rt
+
+
+class DeviceMesh:
+    """Icosphere resident in HBM: unit-sphere float4 positions (+ radius), optional int32 cells
+    and neighbour table.  Vertex order = meshzoo order = the reference's `points` order."""
+
+    def __init__(self, k, xyz, radius=1.0, cells=None, adj=None, v_begin=0):
+        self.k = int(k)
+        self.xyz = xyz                  # float32 [n,4] unit sphere
+        self.radius = float(radius)
+        self.cells = cells              # int32 [T,3] or None
+        self.adj = adj                  # int32 [V,6] or None
+        self.v_begin = int(v_begin)     # first global vertex id held (multi-GPU shards)
+
+    @property
+    def n_vertices(self):
+        return self.xyz.shape[0]
+
+    def points_numpy(self):
+        """float64 [V,3] radius-scaled positions, like `points` after nixis.py:249."""
+        p64 = rt.mesh_points(self.k, self.v_begin, self.v_begin + self.n_vertices, f32=False, f64=True,
+                             device=self.xyz.device)[1]
+        return (p64 * self.radius).cpu().numpy()
+
+
+def _device_xyz(verts, mult):
+    """-> (float32 [n,4] CUDA positions, factor the caller must apply to frequencies)."""
+    if isinstance(verts, DeviceMesh):
+        return verts.xyz, verts.radius * mult
+    if isinstance(verts, torch.Tensor):
+        assert verts.is_cuda and verts.dtype == torch.float32 and verts.shape[1] == 4
+        return verts, mult
+    v = np.ascontiguousarray(verts, dtype=np.float64)
+    assert v.ndim == 2 and v.shape[1] == 3, "verts must be [V,3]"
+    return rt.xyz_from_f64(rt.upload(v), mult), 1.0
+
+
+def create_mesh(divisions, device=False, radius=1.0, with_cells=True, verbose=True):
+    """Icosphere in meshzoo.icosa_sphere order (util.py:17-50).
+
+    device=False: (points float64 [V,3] on the unit sphere, cells int64 [T,3]) numpy arrays,
+    the reference's return value.  device=True: a `DeviceMesh` (nothing leaves the GPU).
+    Vertex arithmetic is FP64 on the device, so the numpy points are full double precision."""
+    rt.require_cuda()
+    k = int(divisions)
+    if verbose:
+        print("Generating the mesh...")
+        print(f"k is {k}")
+    t0 = time.perf_counter()
+    if device:
+        xyz, _ = rt.mesh_points(k)
+        cells = rt.mesh_cells(k) if with_cells else None
+        mesh = DeviceMesh(k, xyz, radius, cells)
+        if verbose:
+            torch.cuda.synchronize()
+            print(f"Number of vertices: {xyz.shape[0]:,}")
+            print(f"Number of triangles: {20 * k * k:,}")
+            print(f"Mesh generated in {time.perf_counter() - t0 :.5f} sec")
+        return mesh
+    _, p64 = rt.mesh_points(k, f32=False, f64=True)
+    cells = rt.mesh_cells(k)
+    points = p64.cpu().numpy()
+    cells = cells.cpu().numpy().astype(np.int64)       # meshzoo: dtype=int
+    if verbose:
+        print(f"Number of vertices: {points.shape[0]:,}")
+        print(f"Number of triangles: {cells.shape[0]:,}")
+        print(f"Mesh generated in {time.perf_counter() - t0 :.5f} sec")
+    return points, cells
+
+
+_MODES = {None: 0, "lower": 1, "upper": 2}
+
+
+def rescale(x, lower, upper, mid=None, mode=None, u_min=None, u_max=None):
+    """Re-scale (normalize) an array to a given lower and upper bound (util.py:110-175)."""
+    if mode is not None and mid is None:
+        print("ERROR: Must supply a middle value to use rescale modes.")
+        print("Continuing with unmodified data.")
+        return x
+    if mode not in _MODES:
+        return None          # the reference falls off the end of the function (util.py:161-175)
+    dev_io = isinstance(x, torch.Tensor)
+    xd = x if dev_io else rt.upload_f32(x)
+    x_min, x_max = rt.minmax(xd).tolist()
+    if u_min is not None and u_min < x_min:
+        x_min = u_min
+    if u_max is not None and u_max > x_max:
+        x_max = u_max
+    out = rt.rescale(xd, x_min, x_max, lower, upper, mid, _MODES[mode])
+    return out if dev_io else rt.download_f64(out)
+
+
+def power_rescale(x, mask=None, mode=None, power=1.0, verbose=True, shift=0.0):
+    """Rescale values using a power function (util.py:178-254).  `shift` (extension, default 0)
+    is subtracted from the result, fusing nixis.py:359."""
+    dev_io = isinstance(x, torch.Tensor)
+    xd = x if dev_io else rt.upload_f32(x)
+    x_min, x_max = rt.minmax(xd).tolist()
+    if mode in (0, 1) and mask is not None:
+        md = mask if isinstance(mask, torch.Tensor) else rt.upload(np.ascontiguousarray(mask).view(np.uint8))
+        summary = rt.power_summary(xd, md, int(mode)).tolist()
+        lo, hi = rt.power_bounds(summary, x_min, x_max)
+        sel = int(mode)
+    else:
+        md, lo, hi, sel = None, x_max, x_min, -1
+    if verbose:
+        print("x min:", x_min)
+        print("x max:", x_max)
+        print("mask min:", lo)
+        print("mask max:", hi)
+    out = rt.power_apply(xd, md, sel, lo, hi, power, shift)
+    return out if dev_io else rt.download_f64(out)
+
+
+def find_percent_val(minval, maxval, percent):
+    """Value that is `percent` of the way from minval to maxval (util.py:556-566). Host scalar."""
+    if not 0.0 < percent < 100.0:
+        print("\n" + "    ERROR: Percent must be between 0 and 100.")
+        print("    Defaulting to 50 percent." + "\n")
+        percent = 50.0
+    return minval + ((maxval - minval) * percent / 100.0)
+
+
+def build_adjacency(triangles):
+    """int32 [V,6] neighbour table, -1 padded, rows in the reference's slot order (util.py:591-613)."""
+    if isinstance(triangles, DeviceMesh):
+        triangles.adj = rt.adj_build(triangles.cells, 10 * triangles.k ** 2 + 2)
+        return triangles.adj
+    if isinstance(triangles, torch.Tensor):
+        return rt.adj_build(triangles, (triangles.shape[0] + 4) // 2)
+    tri = np.ascontiguousarray(triangles)
+    V = int((len(tri) + 4) / 2)
+    cells = rt.upload(tri.astype(np.int32, copy=False))
+    return rt.adj_build(cells, V).cpu().numpy()
+
+
+def sort_adjacency(adj):
+    """Order every row as a ring walk (util.py:623-662).  numpy: in place, returns None, like the
+    reference.  DeviceMesh / CUDA tensor: returns the sorted table (DeviceMesh.adj is replaced)."""
+    if isinstance(adj, DeviceMesh):
+        adj.adj = rt.adj_sort(adj.adj)
+        return adj.adj
+    if isinstance(adj, torch.Tensor):
+        return rt.adj_sort(adj)
+    a = np.ascontiguousarray(adj, dtype=np.int32)
+    adj[...] = rt.adj_sort(rt.upload(a)).cpu().numpy()
+    return None

@@ -14,7 +14,11 @@ vertices are exactly 0..11 (`util.py:640-650`), consistent winding
 Layout: [12 corners | 30 edges x (k-1) | 20 faces x (k-1)(k-2)/2 interiors].
 This numpy version is vectorised per face; the CUDA generator
 (nixis_b200/csrc/nxb_mesh.cu) is closed-form per vertex / per triangle and is
-tested for equality against this one.
+tested for BIT equality against this one, so the arithmetic is spelled out:
+  edge point   p = (1 - j/k) * c[i0] + (j/k) * c[i1]                 j = 1..k-1
+  face point   p = ((1 - i/k - j/k) * c0 + (j/k) * c1) + (i/k) * c2   i = 1..k-1, j = 1..k-i-1
+  all points   p / sqrt((x*x + y*y) + z*z)
+every product and sum rounded once to float64, left to right, no FMA.
 """
 import numpy as np
 
@@ -125,9 +129,12 @@ def icosa_sphere(k):
     for f in range(20):
         if nint:
             base = 12 + 30 * (n - 1) + f * nint
-            pts[base: base + nint] = (CORNERS[FACES[f]].T @ bary).T
+            c0, c1, c2 = CORNERS[FACES[f]]
+            # explicit left-to-right products and sums (no BLAS: the CUDA generator
+            # reproduces these roundings one by one)
+            pts[base: base + nint] = (np.outer(bary[0], c0) + np.outer(bary[1], c1)) + np.outer(bary[2], c2)
         tt = _local_to_global(n, f, ftab)
         cells[f * n * n: (f + 1) * n * n] = tt[lc]
-    norms = np.sqrt(np.einsum("ij,ij->i", pts, pts))
-    pts = (pts.T / norms).T
+    norms = np.sqrt((pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1]) + pts[:, 2] * pts[:, 2])
+    pts = pts / norms[:, None]
     return np.ascontiguousarray(pts), cells

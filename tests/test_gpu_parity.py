@@ -1,0 +1,338 @@
+"""GPU parity: the CUDA path (through the reference-named Python surface and the C-ABI) against
+the golden vectors computed by the reference and against the CPU oracle.
+
+Integer work (perm tables, cells, adjacency) is bit-exact.  Floating point is FP32 on the GPU
+versus float64 in the reference; tolerances are max-abs-error relative to the value RANGE of the
+reference result and are written next to each assertion:
+    fBm 7/8 octaves   <= 1e-5      (FP32 input rounding alone is ~1e-6)
+    fBm 12 octaves    <= 4e-5
+    height assembly   <= 2e-5      (pow / division in FP32)
+    erosion, 1 sweep  <= 1e-5 (h); trajectories N<=50 at R=1, N<=5 at Earth radius <= 1e-4
+"""
+import numpy as np
+import pytest
+
+from oracle import icosphere
+
+pytestmark = pytest.mark.gpu
+EARTH_R = 6378100.0
+
+
+def relerr(a, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    rng = ref.max() - ref.min()
+    return np.abs(np.asarray(a, dtype=np.float64) - ref).max() / (rng if rng > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def nx():
+    import torch
+    assert torch.cuda.is_available()
+    import nixis_b200
+    from nixis_b200 import opensimplex, terrain, util, erosion, runtime, pipeline
+    from nixis_b200 import _lib
+    _lib.load()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.osi, ns.terrain, ns.util, ns.erosion, ns.rt, ns.pipeline, ns.torch = opensimplex, terrain, util, erosion, runtime, pipeline, torch
+    return ns
+
+
+# ---------------------------------------------------------------------------------- noise
+@pytest.mark.parametrize("seed", [0, 12345])
+def test_noise3_vs_reference_golden(nx, golden, seed):
+    g = golden("noise")
+    perm, pgi = nx.osi.init(seed)
+    p = g[f"p3_{seed}"]
+    ref = g[f"v3_{seed}"]
+    got = nx.osi.noisearr3d(p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy(), perm, pgi)
+    assert got.dtype == np.float64 and got.shape == ref.shape
+    mag = np.abs(p).max(axis=1)
+    err = np.abs(got - ref)
+    # FP32 carries ~6e-8 relative error on the lattice coordinate: the allowed error grows with |p|
+    # (noise gradient magnitude is < 4 per unit); near cell/region boundaries the reference itself
+    # jumps by up to 5e-5 (it is not a full lattice sum), hence the floor.
+    tol = 6e-5 + 4.0 * 1.2e-7 * mag * 4
+    assert (err <= tol).all(), (err.max(), mag[err.argmax()])
+    small = mag <= 4.0
+    assert np.quantile(err[small], 0.999) < 5e-6
+
+
+@pytest.mark.parametrize("seed", [0, 12345])
+def test_noise2_vs_reference_golden(nx, golden, seed):
+    g = golden("noise")
+    perm, _ = nx.osi.init(seed)
+    p, ref = g[f"p2_{seed}"], g[f"v2_{seed}"]
+    got = nx.osi.noisearr2d(p[:, 0].copy(), p[:, 1].copy(), perm)
+    mag = np.abs(p).max(axis=1)
+    err = np.abs(got - ref)
+    assert (err <= 6e-5 + 4.0 * 1.2e-7 * mag * 4).all(), err.max()
+
+
+def test_noise_scalar_api(nx):
+    perm, pgi = nx.osi.init(12345)
+    assert abs(nx.osi.noise3d(.1, .2, .3, perm, pgi) - 0.4740432999870549) < 2e-6
+    assert abs(nx.osi.noise3d(1.5, -2.25, 3.125, perm, pgi) - 0.32246761289378145) < 2e-6
+    assert abs(nx.osi.noise2d(.1, .2, perm) - 0.2763967589415571) < 2e-6
+    assert nx.osi.noisearr3d(np.zeros(0), np.zeros(0), np.zeros(0), perm, pgi).shape == (0,)
+
+
+# ---------------------------------------------------------------------------------- fBm
+def test_sample_octaves_vs_reference_golden(nx, golden):
+    g = golden("fbm")
+    for k, s, o, R in g["cases"]:
+        k, s, o = int(k), int(s), int(o)
+        pts, _ = icosphere.icosa_sphere(k)
+        perm, pgi = nx.osi.init(s)
+        h = nx.terrain.sample_octaves(pts * R, None, perm, pgi, o, 1.5, 0.4, 2.5, 0.5, R, verbose=False)
+        tag = f"k{k}_s{s}_o{o}_{'earth' if R != 1.0 else 'unit'}"
+        tol = 1e-5 if o <= 8 else 4e-5
+        assert h.dtype == np.float64 and relerr(h, g[tag]) <= tol, (tag, relerr(h, g[tag]))
+
+
+def test_sample_octaves_accumulates_in_place(nx, golden):
+    g = golden("fbm")
+    pts, _ = icosphere.icosa_sphere(8)
+    perm, pgi = nx.osi.init(7)
+    e = np.linspace(-1, 1, len(pts))
+    r = nx.terrain.sample_octaves(pts, e, perm, pgi, 3, 2.0, 0.7, 2.0, 0.45, 1.0, verbose=False)
+    assert r is e                                   # terrain.py:43 `elevations +=`
+    assert relerr(e, g["k8_s7_accum"]) <= 1e-5
+
+
+def test_sample_noise_single_octave(nx, oracle):
+    pts, _ = icosphere.icosa_sphere(8)
+    perm, pgi = nx.osi.init(3)
+    got = nx.terrain.sample_noise(pts, perm, pgi, 2.5, 0.3, 2.0)
+    ref = (oracle.noisearr3d(pts[:, 0] * 2.5, pts[:, 1] * 2.5, pts[:, 2] * 2.5, perm, pgi) + 1) * 0.5 * 0.3 * 2.0
+    assert relerr(got, ref) <= 1e-5
+
+
+def test_fbm_large_mesh_vs_oracle(nx, oracle):
+    """d=320 (1 024 002 vertices, BASELINE config 0), device-generated mesh, 8 octaves."""
+    k = 320
+    mesh = nx.util.create_mesh(k, device=True, verbose=False)
+    perm, pgi = nx.osi.init(0)
+    h = nx.terrain.sample_octaves(mesh, None, perm, pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0, verbose=False)
+    pts = mesh.points_numpy()
+    ref = oracle.sample_octaves(pts, None, perm, pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0)
+    err = np.abs(h.cpu().numpy().astype(np.float64) - ref) / (ref.max() - ref.min())
+    assert err.max() <= 2.5e-5, err.max()             # rare candidate-set flips at FP32 ties
+    assert np.quantile(err, 0.9999) <= 1e-5
+    # linearity in the amplitude (exact: powers of two)
+    h2 = nx.terrain.sample_octaves(mesh, None, perm, pgi, 8, 1.5, 0.8, 2.5, 0.5, 1.0, verbose=False)
+    assert nx.torch.equal(h2, 2 * h)
+
+
+# ---------------------------------------------------------------------------------- mesh
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 33, 100])
+def test_mesh_bit_exact_vs_oracle_generator(nx, k):
+    pts, cells = nx.util.create_mesh(k, verbose=False)
+    rp, rc = icosphere.icosa_sphere(k)
+    assert pts.dtype == np.float64 and cells.dtype == np.int64
+    assert np.array_equal(cells, rc)
+    assert np.array_equal(pts, rp)                  # FP64 on the device, same roundings
+
+
+def test_mesh_shards_concatenate(nx):
+    k = 40
+    full32, full64 = nx.rt.mesh_points(k, f64=True)
+    V = full32.shape[0]
+    cuts = [0, 5, 12, 500, V // 2, V]
+    parts = [nx.rt.mesh_points(k, a, b, f64=True) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert nx.torch.equal(nx.torch.cat([p[0] for p in parts]), full32)
+    assert nx.torch.equal(nx.torch.cat([p[1] for p in parts]), full64)
+    cells = nx.rt.mesh_cells(k)
+    T = cells.shape[0]
+    parts = [nx.rt.mesh_cells(k, a, b) for a, b in ((0, 7), (7, T // 3), (T // 3, T))]
+    assert nx.torch.equal(nx.torch.cat(parts), cells)
+
+
+# ---------------------------------------------------------------------------------- adjacency
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8, 17, 32])
+def test_adjacency_exact_vs_reference_golden(nx, golden, k):
+    g = golden("adjacency")
+    _, cells = icosphere.icosa_sphere(k)
+    adj = nx.util.build_adjacency(cells)
+    assert adj.dtype == np.int32 and np.array_equal(adj, g[f"unsorted_k{k}"])
+    if k >= 2:
+        r = nx.util.sort_adjacency(adj)
+        assert r is None and np.array_equal(adj, g[f"sorted_k{k}"])     # in place, util.py:650,662
+
+
+def test_adjacency_large_vs_oracle(nx, oracle):
+    k = 200
+    mesh = nx.util.create_mesh(k, device=True, verbose=False)
+    adj_u = nx.util.build_adjacency(mesh).cpu().numpy()
+    adj_s = nx.util.sort_adjacency(mesh).cpu().numpy()
+    cells = mesh.cells.cpu().numpy().astype(np.int64)
+    ref = oracle.build_adjacency(cells)
+    assert np.array_equal(adj_u, ref)
+    oracle.sort_adjacency(ref)
+    assert np.array_equal(adj_s, ref)
+
+
+def test_adjacency_properties_full_size(nx):
+    """d=1000 (10 M vertices): symmetry and ring property, checked on the device."""
+    torch = nx.torch
+    k = 1000
+    mesh = nx.util.create_mesh(k, device=True, verbose=False)
+    nx.util.build_adjacency(mesh)
+    adj = nx.util.sort_adjacency(mesh).long()
+    V = adj.shape[0]
+    assert V == 10 * k * k + 2
+    assert (adj[:12, 5] == -1).all() and (adj[:12, :5] >= 0).all() and (adj[12:] >= 0).all()
+    # checksum of checksums: every directed edge has its reverse
+    src = torch.arange(V, device=adj.device).unsqueeze(1).expand(-1, 6)
+    valid = adj >= 0
+    fwd = (src[valid] * V + adj[valid])
+    bwd = (adj[valid] * V + src[valid])
+    assert torch.equal(torch.sort(fwd).values, torch.sort(bwd).values)
+    # ring: consecutive entries of a sorted row are themselves neighbours
+    for s in range(5):
+        a, b = adj[12:, s], adj[12:, s + 1]
+        assert (adj[a] == b.unsqueeze(1)).any(dim=1).all()
+
+
+def test_adjacency_overflow_reported(nx):
+    cells = np.array([[0, 1, 2]] * 7, dtype=np.int64)       # vertex 0 gets 7 outgoing edges
+    with pytest.raises(Exception):
+        nx.rt.adj_build(nx.rt.upload(cells.astype(np.int32)), 3)
+
+
+# ---------------------------------------------------------------------------------- assembly
+def test_rescale_modes_vs_reference_golden(nx, golden):
+    g = golden("assembly")
+    x = g["rs_x"]
+    assert relerr(nx.util.rescale(x, -1.0, 3.0), g["rs_plain"]) <= 1e-6
+    assert relerr(nx.util.rescale(x, -2.0, 5.0, mid=0.25), g["rs_mid"]) <= 1e-6
+    assert relerr(nx.util.rescale(x, -2.0, 5.0, mid=0.25, mode="lower"), g["rs_lower"]) <= 1e-6
+    assert relerr(nx.util.rescale(x, -2.0, 5.0, mid=0.25, mode="upper"), g["rs_upper"]) <= 1e-6
+    assert relerr(nx.util.rescale(x, 0.0, 1.0, u_min=-10.0, u_max=0.5), g["rs_umin"]) <= 1e-6
+    assert nx.util.rescale(x, 0.0, 1.0, mode="lower") is x          # util.py:155-160 error path
+
+
+def test_power_rescale_vs_reference_golden(nx, golden):
+    g = golden("assembly")
+    x, m = g["rs_x"], g["pr_mask"]
+    for mode, power, key in ((1, 1.7, "pr_m1"), (0, 0.3, "pr_m0")):
+        got = nx.util.power_rescale(x, m, mode, power, verbose=False)
+        ref = g[key]
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert relerr(got[ok], ref[ok]) <= 2e-6
+    assert np.allclose(nx.util.power_rescale(g["pq_x"], g["pq_mask"], 1, 2.0, verbose=False), g["pq_m1"], atol=1e-5)
+    # the sequential if/elif quirk (util.py:203-207): mask_upper ends at 2, not 3
+    assert np.allclose(nx.util.power_rescale(g["pq2_x"], g["pq2_mask"], 1, 2.0, verbose=False), g["pq2_m1"], atol=1e-5)
+    assert np.allclose(nx.util.power_rescale(g["pq2_x"], ~g["pq2_mask"], 0, 0.5, verbose=False), g["pq2_m0"], atol=1e-5)
+    assert np.array_equal(nx.util.power_rescale(x, m, None, 3.0, verbose=False), x.astype(np.float32).astype(np.float64))
+
+
+def test_power_summary_ordered_reduction(nx, oracle):
+    """The one-pass ordered device reduction reproduces the sequential scan on 3 M elements."""
+    rng = np.random.default_rng(11)
+    n = 3_000_001
+    x = np.round(rng.normal(size=n), 3).astype(np.float32)
+    sel = rng.random(n) < 0.3
+    x[:5] = [2.0, 1.5, 1.0, 0.5, 0.25]        # selected prefix of strict records
+    sel[:5] = True
+    xd, md = nx.rt.upload(x), nx.rt.upload(sel.view(np.uint8))
+    for mode in (1, 0):
+        s = nx.rt.power_summary(xd, md, mode).tolist()
+        lo, hi = nx.rt.power_bounds(s, float(x.min()), float(x.max()))
+        _, stats = oracle.power_rescale(x.astype(np.float64), sel, mode, 1.0, return_stats=True)
+        assert (lo, hi) == (stats[2], stats[3])
+
+
+def test_height_assembly_chain_vs_reference_golden(nx, golden):
+    g = golden("assembly")
+    for t in ("k16_s12345", "k32_s0"):
+        raw = g[f"{t}_raw"]
+        h = nx.util.rescale(raw, -4000, 8850)
+        assert relerr(h, g[f"{t}_rescaled"]) <= 1e-6
+        level = nx.util.find_percent_val(np.amin(h), np.amax(h), 55.0)
+        assert abs(level - g[f"{t}_level"]) <= 1e-2
+        ocean = nx.terrain.make_bool_elevation_mask(h, level)
+        ref_ocean = g[f"{t}_ocean"]
+        flips = ocean != ref_ocean
+        # mask may only differ where the reference height is within FP32 rounding of the level
+        assert (np.abs(g[f"{t}_rescaled"][flips] - g[f"{t}_level"]) < 1e-2).all()
+        h = nx.util.power_rescale(h, mask=ref_ocean, mode=1, power=0.5, verbose=False)
+        assert relerr(h, g[f"{t}_pow1"]) <= 2e-5
+        h = nx.util.power_rescale(h, mask=ref_ocean, mode=0, power=2.0, verbose=False)
+        assert relerr(h, g[f"{t}_pow0"]) <= 2e-5
+        h -= level
+        h = nx.util.rescale(h, -4000, 8850, mid=0)
+        assert relerr(h, g[f"{t}_final"]) <= 2e-5
+        # fused device chain (pipeline.assemble_heights)
+        hd, od, lvl = nx.pipeline.assemble_heights(nx.rt.upload_f32(raw))
+        same = od.cpu().numpy().view(np.bool_) == ref_ocean
+        assert abs(lvl - g[f"{t}_level"]) <= 1e-2
+        assert relerr(hd.cpu().numpy()[same], g[f"{t}_final"][same]) <= 2e-5
+        assert (~same).sum() <= 2
+
+
+# ---------------------------------------------------------------------------------- erosion
+@pytest.mark.parametrize("k,seed,R,steps", [(8, 12345, 1.0, (1, 5, 11, 50)), (32, 12345, 1.0, (1, 5, 11, 50)),
+                                            (32, 0, EARTH_R, (1, 3, 5))])
+def test_erosion3_vs_reference_golden(nx, golden, k, seed, R, steps):
+    g = golden("erosion")
+    pts, cells = icosphere.icosa_sphere(k)
+    nodes = pts * R
+    adj = nx.util.build_adjacency(cells)
+    nx.util.sort_adjacency(adj)
+    t = f"k{k}_s{seed}_{'earth' if R != 1.0 else 'unit'}"
+    h0 = g[f"{t}_h0"]
+    # single sweep through the reference-named function, numpy in place
+    h, wat, sed = h0.copy(), np.full_like(h0, 0.3 / 320), np.zeros_like(h0)
+    nx.erosion.erosion_iteration3(nodes, adj, h, wat, sed)
+    assert relerr(h, g[f"{t}_it3_n1_h"]) <= 1e-5
+    assert np.abs(wat - g[f"{t}_it3_n1_w"]).max() <= 1e-5 * np.abs(g[f"{t}_it3_n1_w"]).max()
+    assert np.abs(sed - g[f"{t}_it3_n1_s"]).max() <= 1e-5 * max(np.abs(g[f"{t}_it3_n1_s"]).max(), 1e-30) + 1e-9
+    # trajectories through the driver
+    for n in steps:
+        h = h0.copy()
+        w, s = nx.erosion.erode_terrain3(nodes, adj, h, num_iter=n, verbose=False, return_state=True)
+        ref_h = g[f"{t}_it3_n{n}_h"]
+        assert relerr(h, ref_h) <= 1e-4, (n, relerr(h, ref_h))
+        assert np.abs(w - g[f"{t}_it3_n{n}_w"]).max() <= 1e-4 * np.abs(g[f"{t}_it3_n{n}_w"]).max(), n
+    if R == 1.0:
+        h = h0.copy()
+        assert nx.erosion.erode_terrain3(nodes, adj, h, num_iter=11, verbose=False) is None
+        assert relerr(h, g[f"{t}_driver11_h"]) <= 1e-4
+
+
+@pytest.mark.parametrize("k,seed,R", [(8, 12345, 1.0), (32, 12345, 1.0), (32, 0, EARTH_R)])
+def test_erosion1_vs_reference_golden(nx, golden, k, seed, R):
+    g = golden("erosion")
+    pts, cells = icosphere.icosa_sphere(k)
+    adj = nx.util.build_adjacency(cells)
+    nx.util.sort_adjacency(adj)
+    t = f"k{k}_s{seed}_{'earth' if R != 1.0 else 'unit'}"
+    h0 = g[f"{t}_h0"]
+    w = np.ones_like(h0)
+    r = nx.erosion.erosion_iteration1(adj, h0.copy(), w)
+    assert r is w and relerr(w, g[f"{t}_it1_n1"]) <= 1e-6
+    h = h0.copy()
+    r = nx.erosion.erode_terrain1(pts, adj, h, num_iter=100, verbose=False)
+    assert r is h and relerr(h, g[f"{t}_it1_n100"]) <= 1e-5
+
+
+def test_erosion_large_single_step_vs_oracle(nx, oracle):
+    """d=320, one sweep from identical FP32-rounded state, device-resident path."""
+    k = 320
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    h, _, _ = pipe.heights()
+    h0 = h.cpu().numpy().astype(np.float64)
+    st = pipe.erosion_state(h.clone())
+    st.step()
+    pts = pipe.mesh.points_numpy()
+    adj = pipe.adj.cpu().numpy()
+    wat = np.full_like(h0, np.float32(0.3 / 320), dtype=np.float64)
+    hr, sr = h0.copy(), np.zeros_like(h0)
+    oracle.erosion_iteration3(pts, adj, hr, wat, sr)
+    assert relerr(st.heights.cpu().numpy(), hr) <= 1e-5
+    assert np.abs(st.water.cpu().numpy() - wat).max() <= 2e-5 * np.abs(wat).max()
