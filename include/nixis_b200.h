@@ -125,14 +125,29 @@ int nxb_power_apply_f32(const float *x, const uint8_t *mask, int64_t n, int sel_
                         float lo, float hi, float power, float shift, float *out, void *stream);
 
 /* ---- erosion.py ---------------------------------------------------------- */
-/* erosion.py:197-279 erosion_iteration3 for vertices [v_begin, v_end), FP32 state,
- * ping-pong buffers (reads *_in, writes *_out; no copy-back pass).  `rain` is added to
- * every water value read (erosion.py:182-183 `water += rain_amount` fused).  `radius`
- * scales unit-sphere distances (nodes are radius-scaled in the reference). */
-int nxb_erode3_step_f32(const nxb_float4 *xyz_unit, const int32_t *adj,
-                        const float *h_in, const float *w_in, const float *s_in,
-                        float *h_out, float *w_out, float *s_out,
-                        int64_t v_begin, int64_t v_end, float rain, float radius, void *stream);
+/* erosion.py:34-40 calc_distance for every adjacency slot, once, in FP64, stored as FP32:
+ * dist[v*6+q] = |nodes[v] - nodes[adj[v][q]]| (0 for -1 pads).  The reference measures distances on
+ * the undisplaced sphere positions (erosion.py:227-229), so they are constant over the run. */
+int nxb_edge_lengths_f64(const double *nodes /*[.][3]*/, const int32_t *adj, int64_t n_own, float *dist, void *stream);
+/* same for the closed-form icosphere, rows [v_begin, v_end) with GLOBAL vertex ids in adj_rows */
+int nxb_mesh_icosa_edge_lengths(int k, const int32_t *adj_rows, int64_t v_begin, int64_t v_end, double radius,
+                                float *dist, void *stream);
+/* Tile plan of the sweep (see csrc/nxb_erosion_plan.cuh): per 256-vertex tile the contiguous halo
+ * segments to stage in shared memory and the adjacency re-encoded as 16-bit tile-local codes.
+ * adj: int32[n_own][6] with indices in [0, capacity) (own vertices first, then halo slots of a
+ * multi-GPU shard).  capacity = allocated ELEMENTS of every h/w/s buffer later passed to the step
+ * (multiple of 256, >= round_up(n_own, 256)).  plan_mem: nxb_erode_plan_bytes(n_own) bytes, 16-byte
+ * aligned.  stats_host (nullable) int32[3]: tiles, irregular tiles, max halo slots.  Synchronous. */
+int64_t nxb_erode_plan_bytes(int64_t n_own);
+int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, void *plan_mem,
+                         int32_t *stats_host, void *stream);
+/* erosion.py:197-279 erosion_iteration3 for vertices [0, n_own), FP32 state, ping-pong buffers
+ * (reads *_in, writes *_out; no copy-back pass).  `rain` is added to every water value read
+ * (erosion.py:182-183 `water += rain_amount` fused).  dist: float[round_up(n_own,256)*6]. */
+int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+                             const float *h_in, const float *w_in, const float *s_in,
+                             float *h_out, float *w_out, float *s_out,
+                             int64_t n_own, float rain, void *stream);
 /* erosion.py:76-99 erosion_iteration1 */
 int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
                         int64_t v_begin, int64_t v_end, void *stream);

@@ -41,7 +41,11 @@ SIGNATURES = {
     "nxb_rescale_f32": (_i, [_p, _i64, _f, _f, _f, _f, _i, _f, _i, _p, _p]),
     "nxb_power_summary_f32": (_i, [_p, _p, _i64, _i, _p, _p]),
     "nxb_power_apply_f32": (_i, [_p, _p, _i64, _i, _f, _f, _f, _f, _p, _p]),
-    "nxb_erode3_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _f, _p]),
+    "nxb_edge_lengths_f64": (_i, [_p, _p, _i64, _p, _p]),
+    "nxb_mesh_icosa_edge_lengths": (_i, [_i, _p, _i64, _i64, _d, _p, _p]),
+    "nxb_erode_plan_bytes": (_i64, [_i64]),
+    "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
+    "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "nxb_gather_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_scatter_f32": (_i, [_p, _p, _i64, _p, _p]),

@@ -74,10 +74,10 @@ NXB_API int nxb_adj_build(const int32_t *cells, int64_t T, int64_t V, int32_t *a
     unsigned long long *keys = (unsigned long long *)((char *)workspace + ws_keys_offset(V));
     NXB_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_keys_offset(V), st));
     if (T > 0) {
-        adj_collect_kernel<<<nxb_grid_for(T, 256, 8), 256, 0, st>>>(cells, T, V, count, overflow, keys);
+        adj_collect_kernel<<<nxb_grid_resident(adj_collect_kernel, 256, 0, ((T) + 256 - 1) / 256), 256, 0, st>>>(cells, T, V, count, overflow, keys);
         NXB_LAUNCH_CHECK();
     }
-    adj_rank_kernel<<<nxb_grid_for(V, 256, 8), 256, 0, st>>>(V, count, keys, adj);
+    adj_rank_kernel<<<nxb_grid_resident(adj_rank_kernel, 256, 0, ((V) + 256 - 1) / 256), 256, 0, st>>>(V, count, keys, adj);
     NXB_LAUNCH_CHECK();
     int32_t flag = 0;
     NXB_CUDA(cudaMemcpyAsync(&flag, overflow, sizeof flag, cudaMemcpyDeviceToHost, st));
@@ -142,7 +142,7 @@ NXB_API int nxb_adj_sort(const int32_t *adj_in, int32_t *adj_out, int64_t V, voi
     NXB_ARG(V >= 0);
     if (V == 0) return NXB_OK;
     NXB_ARG(adj_in && adj_out && adj_in != adj_out);
-    adj_sort_kernel<<<nxb_grid_for(V, 256, 8), 256, 0, (cudaStream_t)stream>>>(adj_in, adj_out, V);
+    adj_sort_kernel<<<nxb_grid_resident(adj_sort_kernel, 256, 0, ((V) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(adj_in, adj_out, V);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

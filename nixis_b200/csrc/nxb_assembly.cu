@@ -44,7 +44,7 @@ NXB_API int nxb_minmax_f32(const float *x, int64_t n, float *minmax, void *strea
     NXB_ARG(n >= 0 && minmax);
     if (n == 0) return NXB_OK;
     NXB_ARG(x);
-    minmax_kernel<<<nxb_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, n, minmax);
+    minmax_kernel<<<nxb_grid_resident(minmax_kernel, 256, 0, (((n + 3) / 4) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, minmax);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -93,7 +93,7 @@ NXB_API int nxb_rescale_f32(const float *x, int64_t n, float x_min, float x_max,
     if (n == 0) return NXB_OK;
     NXB_ARG(x && out);
     RescaleArgs a = {x_min, x_max, lower, upper, mid, has_mid, mode};
-    rescale_kernel<<<nxb_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, n, a, out);
+    rescale_kernel<<<nxb_grid_resident(rescale_kernel, 256, 0, (((n + 3) / 4) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, a, out);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -123,7 +123,7 @@ NXB_API int nxb_mask_le_f32(const float *h, int64_t n, float level, uint8_t *mas
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(h && mask);
-    mask_le_kernel<<<nxb_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(h, n, level, mask);
+    mask_le_kernel<<<nxb_grid_resident(mask_le_kernel, 256, 0, (((n + 3) / 4) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(h, n, level, mask);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -242,7 +242,7 @@ NXB_API int nxb_power_summary_f32(const float *x, const uint8_t *mask, int64_t n
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
     NXB_ARG(dev < 64);
-    int grid = nxb_grid_for((n + PSTAT_PER_THREAD - 1) / PSTAT_PER_THREAD, PSTAT_BLOCK, 4);
+    int grid = nxb_grid_resident(power_stats_kernel, PSTAT_BLOCK, 0, (n + PSTAT_BLOCK * PSTAT_PER_THREAD - 1) / (PSTAT_BLOCK * PSTAT_PER_THREAD));
     PStatScratch &sc = g_pstat[dev];
     if (sc.cap < grid) {
         if (sc.blocks) cudaFree(sc.blocks);
@@ -285,7 +285,7 @@ NXB_API int nxb_power_apply_f32(const float *x, const uint8_t *mask, int64_t n, 
     if (n == 0) return NXB_OK;
     NXB_ARG(x && out && (mask || sel_mode == -1));
     // sel_mode -1 is mode=None: no element is selected (util.py:224-252 never fire)
-    power_apply_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, mask, n, sel_mode, lo, hi, power, shift, out);
+    power_apply_kernel<<<nxb_grid_resident(power_apply_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(x, mask, n, sel_mode, lo, hi, power, shift, out);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -307,7 +307,7 @@ NXB_API int nxb_f32_to_f64(const float *src, int64_t n, double *dst, void *strea
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(src && dst);
-    f32_to_f64_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    f32_to_f64_kernel<<<nxb_grid_resident(f32_to_f64_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -317,7 +317,7 @@ NXB_API int nxb_f64_to_f32(const double *src, int64_t n, float *dst, void *strea
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(src && dst);
-    f64_to_f32_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    f64_to_f32_kernel<<<nxb_grid_resident(f64_to_f32_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -339,7 +339,7 @@ NXB_API int nxb_gather_f32(const float *src, const int32_t *idx, int64_t n, floa
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(src && idx && dst);
-    gather_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+    gather_kernel<<<nxb_grid_resident(gather_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -349,7 +349,7 @@ NXB_API int nxb_scatter_f32(const float *src, const int32_t *idx, int64_t n, flo
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(src && idx && dst);
-    scatter_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+    scatter_kernel<<<nxb_grid_resident(scatter_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

@@ -48,6 +48,53 @@ static inline int nxb_grid_for(int64_t n, int block, int max_ctas_per_sm)
     return (int)(need < cap ? need : cap);
 }
 
+// Persistent grid for kernel `k`: as many CTAs as are co-resident (occupancy API), never more
+// than the work needs.  A fixed "8 CTAs per SM" guess leaves a second, under-occupied wave when
+// the register budget allows fewer (seen in profiles/r01_ncu_summary.json: 1184 CTAs launched,
+// 888 resident).
+template <typename K>
+static inline int nxb_grid_resident(K k, int block, size_t dyn_smem, int64_t n_blocks_of_work)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t cap = (int64_t)nxb_sm_count() * per_sm;
+    if (n_blocks_of_work < 1) n_blocks_of_work = 1;
+    return (int)(n_blocks_of_work < cap ? n_blocks_of_work : cap);
+}
+
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ----------------------
+__device__ __forceinline__ uint32_t nxb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void nxb_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nxb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nxb_fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nxb_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nxb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool nxb_mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(nxb_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void nxb_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!nxb_mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completes on `bar`
+__device__ __forceinline__ void nxb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(nxb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(nxb_smem_u32(bar)) : "memory");
+}
+
 // float atomic min/max through the ordered-int trick (works for all finite + inf)
 __device__ __forceinline__ void atomic_min_f32(float *addr, float v)
 {

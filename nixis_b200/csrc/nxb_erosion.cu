@@ -1,76 +1,344 @@
-// Erosion sweeps over the ELL neighbour table -- erosion.py:34-40, 76-99, 197-279.
+// Erosion sweeps -- erosion.py:34-40, 76-99, 197-279 -- as a shared-memory-staged stencil.
 //
-// HBM-bound stencil.  Algorithmic traffic per vertex-iteration of iteration3:
-//   own h,w,s read 12 B + h,w,s write 12 B + adjacency row 24 B + own xyz 12 B = 60 B;
-// neighbour values are some other vertex's compulsory read and come from L1/L2: the meshzoo
-// order is row-major inside each icosahedron face, so the 6 neighbours of vertex v are
-// v+-1 and two short runs one mesh row above / below.
+// HBM-bound.  Algorithmic traffic per vertex-iteration of erosion_iteration3:
+//   own h,w,s read 12 B + write 12 B + adjacency row 24 B + own position 12 B = 60 B.
+// What this implementation actually streams per vertex-iteration:
+//   h,w,s read 12 B + write 12 B + 16-bit tile-local adjacency 12 B + 6 edge lengths 24 B = 60 B.
 //
-// Ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
-// 274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
+// History (profiles/r01_ncu_summary.json): v1, one thread per vertex with 18 global gathers
+// (xyz, h, w of 6 neighbours), ran at 45 % of HBM peak with minimal DRAM traffic -- latency bound;
+// v2 streamed the tile's own data with cp.async.bulk but kept the gathers and was then bound by
+// gather latency + instruction issue (322 instr/vertex, six IEEE sqrt sequences, L1 squeezed out by
+// the shared-memory carve-out).  v3 (this file) removes both:
+//
+//   * EDGE LENGTHS ARE PRECOMPUTED once, in FP64, and stored as FP32 (erosion.py:227-229 uses the
+//     undisplaced sphere positions, so they never change).  No neighbour positions are read and no
+//     sqrt is evaluated in the sweep; it also removes the cancellation error of differencing FP32
+//     positions (relative 1e-4 at d=2500).
+//   * TILE PLAN (nxb_erosion_plan.cuh): for each tile of 256 consecutive vertices the neighbours
+//     are the tile itself plus <= 6 contiguous index runs (mesh rows above / below, the elements
+//     next to the tile ends).  A producer warp brings the tile's own streams AND those runs of
+//     h / w into shared memory with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an
+//     mbarrier, ERO_STAGES tiles ahead; eight consumer warps then read every neighbour value from
+//     shared memory through a 16-bit tile-local adjacency.  No global gathers, no L1 dependence.
+//     The halo runs were just streamed by a neighbouring tile, so they come from L2, not HBM.
+//   * ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
+//     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
 #include "nxb_common.cuh"
+#include "nxb_erosion_plan.cuh"
 
-__device__ __forceinline__ void load_adj_row(const int32_t *__restrict__ adj, int64_t v, int32_t (&row)[6])
-{
-    const int2 *p = reinterpret_cast<const int2 *>(adj + v * 6);
-    int2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    row[0] = a.x; row[1] = a.y; row[2] = b.x; row[3] = b.y; row[4] = c.x; row[5] = c.y;
-}
+#define ERO_STAGES 4
+#define ERO_CONSUMER_WARPS (ERO_TILE / 32)
+#define ERO_THREADS (ERO_TILE + 32)
 
-__global__ void __launch_bounds__(256)
-erode3_kernel(const float4 *__restrict__ xyz, const int32_t *__restrict__ adj,
-              const float *__restrict__ h_in, const float *__restrict__ w_in, const float *__restrict__ s_in,
-              float *__restrict__ h_out, float *__restrict__ w_out, float *__restrict__ s_out,
-              int64_t v_begin, int64_t v_end, float rain, float radius)
+struct __align__(128) EroStage {
+    float h[ERO_STAGE_ELEMS];           // [own tile | halo segments]
+    float w[ERO_STAGE_ELEMS];
+    float s[ERO_TILE];
+    float dist[ERO_TILE * 6];
+    uint16_t adj[ERO_TILE * 6];
+    int32_t irregular;
+    int32_t pad[31];
+};
+
+struct EroPlanArgs {
+    const EroTileDesc *desc; const uint16_t *adj16;     // plan
+    const int32_t *adj;                                 // int32 ELL (irregular tiles only)
+    const float *dist;
+    const float *h_in, *w_in, *s_in;
+    float *h_out, *w_out, *s_out;
+    int64_t n_own;
+    float rain;
+};
+
+// erosion.py:210-267 for one vertex, neighbour values already fetched.
+__device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i, const float (&hn)[6],
+                                            const float (&wn)[6], const float (&d)[6], float rain,
+                                            float &hh, float &ww, float &ss)
 {
     const float evaporation = (float)(0.1 / 320), solubility = (float)(0.01 / 320), capacity = (float)(0.2 / 320);
-    for (int64_t i = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_end;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t row[6];
-        load_adj_row(adj, i, row);
-        const float4 pi = __ldg(xyz + i);
-        const float me = h_in[i];
-        const float wat_i = w_in[i] + rain;
-        const float sed_i = s_in[i];
-        float sed_amt = sed_i, wat_amt = wat_i;
+    const float wat_i = wat_own + rain;
+    float sed_amt = sed_i, wat_amt = wat_i;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int32_t n = row[q];
-            if (n < 0) continue;
-            const float4 pn = __ldg(xyz + n);
-            const float hn = __ldg(h_in + n);
-            const float wn = __ldg(w_in + n) + rain;
-            const float ax = pi.x - pn.x, ay = pi.y - pn.y, az = pi.z - pn.z;
-            const float d = radius * sqrtf(ax * ax + ay * ay + az * az);
-            // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0
-            const float dh = hn - me;
-            if (dh > 0.0f)      { sed_amt += solubility * wn; wat_amt += wn * d; }
-            else if (dh < 0.0f) { sed_amt -= solubility * wn; wat_amt -= wn * d; }
+    for (int q = 0; q < 6; ++q) {
+        const float wq = wn[q] + rain;
+        // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0
+        const float dh = hn[q] - me;
+        if (dh > 0.0f)      { sed_amt += solubility * wq; wat_amt += wq * d[q]; }
+        else if (dh < 0.0f) { sed_amt -= solubility * wq; wat_amt -= wq * d[q]; }
+    }
+    hh = me - sed_amt;
+    ss = sed_i + sed_amt;
+    ww = wat_i + (wat_amt - wat_amt * evaporation);
+    const float cw = capacity * ww;
+    if (ss > cw) { hh += ss - cw; ss -= ss - cw; }
+}
+
+__global__ void __launch_bounds__(ERO_THREADS)
+erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    EroStage *stage = reinterpret_cast<EroStage *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[ERO_STAGES], empty[ERO_STAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.n_own + ERO_TILE - 1) / ERO_TILE;
+    const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < ERO_STAGES; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
+        nxb_fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
+        const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
+        int32_t word = 0;                       // this lane's word of the 16-word descriptor
+        if (my_tiles > 0 && lane < 16) word = __ldg(dw + (int64_t)blockIdx.x * 16 + lane);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int s = (int)(it % ERO_STAGES);
+            const int64_t tile = blockIdx.x + it * gridDim.x;
+            const int64_t v0 = tile * ERO_TILE;
+            // descriptor words: 0..5 seg_start | 6..8 seg_len pairs | 9..11 seg_off pairs | 12 nseg | 13 irregular | 14 halo_used
+            const int32_t cur = word;
+            if (it + 1 < my_tiles && lane < 16) word = __ldg(dw + (tile + gridDim.x) * 16 + lane);
+            const int nseg = __shfl_sync(0xffffffffu, cur, 12);
+            const int irregular = __shfl_sync(0xffffffffu, cur, 13);
+            const int halo_used = __shfl_sync(0xffffffffu, cur, 14);
+            const int q = lane - 1;             // segment handled by this lane
+            const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
+            const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
+            const uint32_t lens = (uint32_t)__shfl_sync(0xffffffffu, cur, 6 + (qq >> 1));
+            const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, 9 + (qq >> 1));
+            const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
+            const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
+            nxb_mbar_wait(&empty[s], (uint32_t)(((it / ERO_STAGES) & 1) ^ 1));
+            EroStage &st = stage[s];
+            if (lane == 0) {
+                st.irregular = irregular;
+                const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
+                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
+                nxb_bulk_g2s(st.h, a.h_in + v0, ERO_TILE * 4, &full[s]);
+                nxb_bulk_g2s(st.w, a.w_in + v0, ERO_TILE * 4, &full[s]);
+                nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
+                nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
+                nxb_bulk_g2s(st.adj, a.adj16 + v0 * 6, ERO_TILE * 12, &full[s]);
+            } else if (q < nseg && !irregular) {
+                nxb_bulk_g2s(st.h + ERO_TILE + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
+                nxb_bulk_g2s(st.w + ERO_TILE + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+            }
+            __syncwarp();
         }
-        float hh = me - sed_amt;
-        float ss = sed_i + sed_amt;
-        float ww = wat_i + (wat_amt - wat_amt * evaporation);
-        const float cw = capacity * ww;
-        if (ss > cw) { hh += ss - cw; ss -= ss - cw; }
-        h_out[i] = hh; w_out[i] = ww; s_out[i] = ss;
+    } else {
+        // ---------------- consumer warps: thread c owns vertex v0 + c of every tile of this CTA
+        const int c = tid - 32;
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int s = (int)(it % ERO_STAGES);
+            const int64_t v = (blockIdx.x + it * gridDim.x) * (int64_t)ERO_TILE + c;
+            nxb_mbar_wait(&full[s], (uint32_t)((it / ERO_STAGES) & 1));
+            const EroStage &st = stage[s];
+            float hn[6], wn[6], d[6];
+            {
+                const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
+                const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
+                d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+            }
+            const float me = st.h[c], wo = st.w[c], so = st.s[c];
+            if (!st.irregular) {
+                const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
+                const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
+                const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q]]; wn[q] = st.w[code[q]]; }
+            } else {
+                // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
+                const int64_t vv = v < a.n_own ? v : a.n_own - 1;
+                const int2 *rp = reinterpret_cast<const int2 *>(a.adj + vv * 6);
+                const int2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+                const int32_t row[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
+                    hn[q] = __ldg(a.h_in + n); wn[q] = __ldg(a.w_in + n);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nxb_smem_u32(&empty[s])) : "memory");
+            float hh, ww, ss;
+            erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
+            if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
+        }
     }
 }
 
-NXB_API int nxb_erode3_step_f32(const nxb_float4 *xyz_unit, const int32_t *adj,
-                                const float *h_in, const float *w_in, const float *s_in,
-                                float *h_out, float *w_out, float *s_out,
-                                int64_t v_begin, int64_t v_end, float rain, float radius, void *stream)
+// ---------------------------------------------------------------------------------------------
+// Plan builder: one CTA per tile.  Greedy covering of the tile's out-of-tile neighbour indices by
+// 4-aligned windows of at most ERO_MAXSEG elements, smallest index first.
+__device__ __forceinline__ int block_reduce_min(int v, int *scratch)
 {
-    NXB_ARG(v_begin >= 0 && v_end >= v_begin);
-    if (v_end == v_begin) return NXB_OK;
-    NXB_ARG(xyz_unit && adj && h_in && w_in && s_in && h_out && w_out && s_out);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = min(r, scratch[w]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(ERO_TILE)
+ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity,
+                EroTileDesc *__restrict__ desc, uint16_t *__restrict__ adj16, int32_t *__restrict__ stats)
+{
+    __shared__ int scratch[ERO_TILE / 32];
+    const int64_t tile = blockIdx.x, v0 = tile * ERO_TILE;
+    const int c = threadIdx.x;
+    const int64_t v = v0 + c;
+    int32_t nb[6];
+    uint32_t code[6];
+    bool open[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        nb[q] = v < n_own ? adj[v * 6 + q] : -1;
+        open[q] = false;
+        if (nb[q] < 0) code[q] = (uint32_t)c;                                  // pad: the vertex itself
+        else if (nb[q] >= v0 && nb[q] < v0 + ERO_TILE) code[q] = (uint32_t)(nb[q] - v0);
+        else { code[q] = 0; open[q] = true; }
+    }
+    EroTileDesc d;
+    for (int k = 0; k < ERO_NSEG; ++k) { d.seg_start[k] = 0; d.seg_len[k] = 0; d.seg_off[k] = 0; }
+    d.nseg = 0; d.irregular = 0; d.halo_used = 0; d.pad = 0;
+    const int BIG = 0x7fffffff;
+    for (int k = 0; k <= ERO_NSEG; ++k) {
+        int m = BIG;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (open[q]) m = min(m, nb[q]);
+        m = block_reduce_min(m, scratch);
+        if (m == BIG) break;                                                    // everything covered
+        if (k == ERO_NSEG) { d.irregular = 1; break; }
+        const int s = m & ~3;
+        // window: at most ERO_MAXSEG elements, and never across the tile itself (the elements just
+        // before and just after the tile must not be merged into one segment spanning it)
+        int wend = s + ERO_MAXSEG;
+        if (s < v0 && wend > v0) wend = (int)v0;
+        int e = -1;                                                             // largest open index inside the window
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (open[q] && nb[q] < wend) e = max(e, nb[q]);
+        e = -block_reduce_min(-e, scratch);
+        const int len = ((e + 1 - s) + 3) & ~3;
+        if (d.halo_used + len > ERO_HALO_CAP || (int64_t)s + len > capacity) { d.irregular = 1; break; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+            if (open[q] && nb[q] < s + len) { code[q] = (uint32_t)(ERO_TILE + d.halo_used + (nb[q] - s)); open[q] = false; }
+        d.seg_start[k] = s; d.seg_len[k] = (uint16_t)len; d.seg_off[k] = (uint16_t)d.halo_used;
+        d.halo_used += len;
+        d.nseg = k + 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles
+    if (c == 0) {
+        desc[tile] = d;
+        if (d.irregular) atomicAdd(stats, 1);
+        atomicMax(stats + 1, d.halo_used);
+    }
+}
+
+NXB_API int64_t nxb_erode_plan_bytes(int64_t n_own)
+{
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    return n_tiles * (int64_t)sizeof(EroTileDesc) + n_tiles * ERO_TILE * 6 * (int64_t)sizeof(uint16_t);
+}
+
+NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, void *plan_mem,
+                                 int32_t *stats_host, void *stream)
+{
+    NXB_ARG(n_own >= 0 && capacity % ERO_TILE == 0 && capacity >= (n_own + ERO_TILE - 1) / ERO_TILE * ERO_TILE);
+    if (n_own == 0) return NXB_OK;
+    NXB_ARG(adj && plan_mem && (((uintptr_t)plan_mem) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    EroTileDesc *desc = (EroTileDesc *)plan_mem;
+    uint16_t *adj16 = (uint16_t *)((char *)plan_mem + n_tiles * sizeof(EroTileDesc));
+    int32_t *stats = nullptr;
+    NXB_CUDA(cudaMalloc(&stats, 8));
+    NXB_CUDA(cudaMemsetAsync(stats, 0, 8, st));
+    ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats);
+    NXB_LAUNCH_CHECK();
+    int32_t h[2] = {0, 0};
+    NXB_CUDA(cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, st));
+    NXB_CUDA(cudaStreamSynchronize(st));
+    NXB_CUDA(cudaFree(stats));
+    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; }
+    return NXB_OK;
+}
+
+static bool g_ero_attr_set[64] = {false};
+
+NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+                                     const float *h_in, const float *w_in, const float *s_in,
+                                     float *h_out, float *w_out, float *s_out,
+                                     int64_t n_own, float rain, void *stream)
+{
+    NXB_ARG(n_own >= 0);
+    if (n_own == 0) return NXB_OK;
+    NXB_ARG(plan_mem && adj && dist && h_in && w_in && s_in && h_out && w_out && s_out);
     NXB_ARG(h_in != h_out && w_in != w_out && s_in != s_out);
-    erode3_kernel<<<nxb_grid_for(v_end - v_begin, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const float4 *)xyz_unit, adj, h_in, w_in, s_in, h_out, w_out, s_out, v_begin, v_end, rain, radius);
+    NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    EroPlanArgs a;
+    a.desc = (const EroTileDesc *)plan_mem;
+    a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
+    a.adj = adj; a.dist = dist;
+    a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
+    a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
+    a.n_own = n_own; a.rain = rain;
+    int dev = 0;
+    NXB_CUDA(cudaGetDevice(&dev));
+    const size_t smem = sizeof(EroStage) * ERO_STAGES;
+    if (dev < 64 && !g_ero_attr_set[dev]) {
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_ero_attr_set[dev] = true;
+    }
+    int grid = nxb_grid_resident(erode3_plan_kernel, ERO_THREADS, smem, n_tiles);
+    erode3_plan_kernel<<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Edge lengths from caller-supplied float64 positions (erosion.py:34-40 calc_distance), FP64
+// arithmetic, FP32 result.  adj rows [0, n_own) index into nodes[.][3].
+__global__ void __launch_bounds__(256)
+edge_lengths_kernel(const double *__restrict__ nodes, const int32_t *__restrict__ adj, int64_t n_own,
+                    float *__restrict__ dist)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_own * 6; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = i / 6;
+        const int32_t n = adj[i];
+        float r = 0.0f;
+        if (n >= 0) {
+            const double ax = nodes[3 * v] - nodes[3 * (int64_t)n], ay = nodes[3 * v + 1] - nodes[3 * (int64_t)n + 1],
+                         az = nodes[3 * v + 2] - nodes[3 * (int64_t)n + 2];
+            r = (float)sqrt(ax * ax + ay * ay + az * az);
+        }
+        dist[i] = r;
+    }
+}
+
+NXB_API int nxb_edge_lengths_f64(const double *nodes, const int32_t *adj, int64_t n_own, float *dist, void *stream)
+{
+    NXB_ARG(n_own >= 0);
+    if (n_own == 0) return NXB_OK;
+    NXB_ARG(nodes && adj && dist);
+    int grid = nxb_grid_resident(edge_lengths_kernel, 256, 0, (n_own * 6 + 255) / 256);
+    edge_lengths_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nodes, adj, n_own, dist);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // erosion.py:76-99
 __global__ void __launch_bounds__(256)
 erode1_kernel(const int32_t *__restrict__ adj, const float *__restrict__ h_in, float *__restrict__ h_out,
@@ -78,17 +346,18 @@ erode1_kernel(const int32_t *__restrict__ adj, const float *__restrict__ h_in, f
 {
     for (int64_t i = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_end;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t row[6];
-        load_adj_row(adj, i, row);
+        const int2 *p = reinterpret_cast<const int2 *>(adj + i * 6);
+        const int2 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+        const int32_t row[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
         const float me = h_in[i];
+        float hn[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) hn[q] = __ldg(h_in + (row[q] < 0 ? i : (int64_t)row[q]));
         float amt = 0.0f;
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-            const int32_t n = row[q];
-            if (n < 0) continue;
-            const float hn = __ldg(h_in + n);
-            if (hn > me) amt += 0.0005f;
-            else if (hn < me) amt -= 0.0005f;
+            if (hn[q] > me) amt += 0.0005f;
+            else if (hn[q] < me) amt -= 0.0005f;
         }
         h_out[i] = me + amt;
     }
@@ -100,7 +369,8 @@ NXB_API int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_
     NXB_ARG(v_begin >= 0 && v_end >= v_begin);
     if (v_end == v_begin) return NXB_OK;
     NXB_ARG(adj && h_in && h_out && h_in != h_out);
-    erode1_kernel<<<nxb_grid_for(v_end - v_begin, 256, 8), 256, 0, (cudaStream_t)stream>>>(adj, h_in, h_out, v_begin, v_end);
+    int grid = nxb_grid_resident(erode1_kernel, 256, 0, (v_end - v_begin + 255) / 256);
+    erode1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adj, h_in, h_out, v_begin, v_end);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

@@ -46,50 +46,95 @@ __device__ __forceinline__ int64_t interior_before_row(int64_t n, int64_t r)
     return (r - 1) * (n - 1) - (r - 1) * r / 2;
 }
 
+// unit-sphere position of vertex v of the k-division icosphere, FP64, roundings as in oracle/icosphere.py
+__device__ __forceinline__ void icosa_point(int64_t n, int64_t v, double &x, double &y, double &z)
+{
+    const int64_t n_edge = 30 * (n - 1), per_face = (n - 1) * (n - 2) / 2;
+    if (v < 12) {
+        x = c_corner[v][0]; y = c_corner[v][1]; z = c_corner[v][2];
+    } else if (v < 12 + n_edge) {
+        int64_t w = v - 12;
+        int e = (int)(w / (n - 1));
+        int64_t j = w % (n - 1) + 1;
+        double t = __ddiv_rn((double)j, (double)n), u = __dsub_rn(1.0, t);
+        const double *a = c_corner[c_edge[e][0]], *b = c_corner[c_edge[e][1]];
+        x = __dadd_rn(__dmul_rn(u, a[0]), __dmul_rn(t, b[0]));
+        y = __dadd_rn(__dmul_rn(u, a[1]), __dmul_rn(t, b[1]));
+        z = __dadd_rn(__dmul_rn(u, a[2]), __dmul_rn(t, b[2]));
+    } else {
+        int64_t w = v - 12 - n_edge;
+        int f = (int)(w / per_face);
+        int64_t q = w % per_face;
+        // row i (1..n-2): largest i with interior_before_row(i) <= q
+        double disc = (double)(2 * n - 3) * (double)(2 * n - 3) - 8.0 * (double)q;
+        int64_t i = (int64_t)(((double)(2 * n - 3) - sqrt(disc)) * 0.5) + 1;
+        if (i < 1) i = 1;
+        if (i > n - 2) i = n - 2;
+        while (i > 1 && interior_before_row(n, i) > q) --i;
+        while (i < n - 2 && interior_before_row(n, i + 1) <= q) ++i;
+        int64_t j = q - interior_before_row(n, i) + 1;
+        double bi = __ddiv_rn((double)i, (double)n), bj = __ddiv_rn((double)j, (double)n);
+        double b0 = __dsub_rn(__dsub_rn(1.0, bi), bj);
+        const double *c0 = c_corner[c_face[f][0]], *c1 = c_corner[c_face[f][1]], *c2 = c_corner[c_face[f][2]];
+        x = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[0]), __dmul_rn(bj, c1[0])), __dmul_rn(bi, c2[0]));
+        y = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[1]), __dmul_rn(bj, c1[1])), __dmul_rn(bi, c2[1]));
+        z = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[2]), __dmul_rn(bj, c1[2])), __dmul_rn(bi, c2[2]));
+    }
+    double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    x = __ddiv_rn(x, nrm); y = __ddiv_rn(y, nrm); z = __ddiv_rn(z, nrm);
+}
+
 __global__ void __launch_bounds__(256)
 icosa_points_kernel(int k, int64_t v_begin, int64_t v_end, float4 *__restrict__ out32, double *__restrict__ out64)
 {
-    const int64_t n = k;
-    const int64_t n_edge = 30 * (n - 1), per_face = (n - 1) * (n - 2) / 2;
     for (int64_t v = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < v_end;
          v += (int64_t)gridDim.x * blockDim.x) {
         double x, y, z;
-        if (v < 12) {
-            x = c_corner[v][0]; y = c_corner[v][1]; z = c_corner[v][2];
-        } else if (v < 12 + n_edge) {
-            int64_t w = v - 12;
-            int e = (int)(w / (n - 1));
-            int64_t j = w % (n - 1) + 1;
-            double t = __ddiv_rn((double)j, (double)n), u = __dsub_rn(1.0, t);
-            const double *a = c_corner[c_edge[e][0]], *b = c_corner[c_edge[e][1]];
-            x = __dadd_rn(__dmul_rn(u, a[0]), __dmul_rn(t, b[0]));
-            y = __dadd_rn(__dmul_rn(u, a[1]), __dmul_rn(t, b[1]));
-            z = __dadd_rn(__dmul_rn(u, a[2]), __dmul_rn(t, b[2]));
-        } else {
-            int64_t w = v - 12 - n_edge;
-            int f = (int)(w / per_face);
-            int64_t q = w % per_face;
-            // row i (1..n-2): largest i with interior_before_row(i) <= q
-            double disc = (double)(2 * n - 3) * (double)(2 * n - 3) - 8.0 * (double)q;
-            int64_t i = (int64_t)(((double)(2 * n - 3) - sqrt(disc)) * 0.5) + 1;
-            if (i < 1) i = 1;
-            if (i > n - 2) i = n - 2;
-            while (i > 1 && interior_before_row(n, i) > q) --i;
-            while (i < n - 2 && interior_before_row(n, i + 1) <= q) ++i;
-            int64_t j = q - interior_before_row(n, i) + 1;
-            double bi = __ddiv_rn((double)i, (double)n), bj = __ddiv_rn((double)j, (double)n);
-            double b0 = __dsub_rn(__dsub_rn(1.0, bi), bj);
-            const double *c0 = c_corner[c_face[f][0]], *c1 = c_corner[c_face[f][1]], *c2 = c_corner[c_face[f][2]];
-            x = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[0]), __dmul_rn(bj, c1[0])), __dmul_rn(bi, c2[0]));
-            y = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[1]), __dmul_rn(bj, c1[1])), __dmul_rn(bi, c2[1]));
-            z = __dadd_rn(__dadd_rn(__dmul_rn(b0, c0[2]), __dmul_rn(bj, c1[2])), __dmul_rn(bi, c2[2]));
-        }
-        double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-        x = __ddiv_rn(x, nrm); y = __ddiv_rn(y, nrm); z = __ddiv_rn(z, nrm);
+        icosa_point(k, v, x, y, z);
         int64_t o = v - v_begin;
         if (out32) out32[o] = make_float4((float)x, (float)y, (float)z, 0.0f);
         if (out64) { out64[3 * o] = x; out64[3 * o + 1] = y; out64[3 * o + 2] = z; }
     }
+}
+
+// Edge lengths of the radius-scaled icosphere for adjacency rows [v_begin, v_end) (GLOBAL vertex ids
+// in adj_rows), positions recomputed in FP64 on the fly: dist[(v - v_begin) * 6 + q] =
+// |R p_v - R p_n| (erosion.py:34-40, 227-229), rounded once to FP32; 0 for -1 pads.
+__global__ void __launch_bounds__(256)
+icosa_edge_lengths_kernel(int k, const int32_t *__restrict__ adj_rows, int64_t v_begin, int64_t v_end, double radius,
+                          float *__restrict__ dist)
+{
+    for (int64_t v = v_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < v_end;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        icosa_point(k, v, x, y, z);
+        x *= radius; y *= radius; z *= radius;
+        const int64_t o = (v - v_begin) * 6;
+        for (int q = 0; q < 6; ++q) {
+            const int32_t n = adj_rows[o + q];
+            float r = 0.0f;
+            if (n >= 0) {
+                double a, b, c;
+                icosa_point(k, n, a, b, c);
+                const double ax = x - a * radius, ay = y - b * radius, az = z - c * radius;
+                r = (float)sqrt(ax * ax + ay * ay + az * az);
+            }
+            dist[o + q] = r;
+        }
+    }
+}
+
+NXB_API int nxb_mesh_icosa_edge_lengths(int k, const int32_t *adj_rows, int64_t v_begin, int64_t v_end, double radius,
+                                        float *dist, void *stream)
+{
+    NXB_ARG(k >= 1 && k <= 14000 && adj_rows && dist);
+    int64_t V = 10 * (int64_t)k * k + 2;
+    NXB_ARG(0 <= v_begin && v_begin <= v_end && v_end <= V);
+    if (v_end == v_begin) return NXB_OK;
+    int grid = nxb_grid_resident(icosa_edge_lengths_kernel, 256, 0, (v_end - v_begin + 255) / 256);
+    icosa_edge_lengths_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, adj_rows, v_begin, v_end, radius, dist);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
 }
 
 // local node (row r, col c) of face f -> global vertex id
@@ -152,7 +197,7 @@ NXB_API int nxb_mesh_icosa_points(int k, int64_t v_begin, int64_t v_end, nxb_flo
     int64_t V = 10 * (int64_t)k * k + 2;
     NXB_ARG(0 <= v_begin && v_begin <= v_end && v_end <= V);
     if (v_end == v_begin) return NXB_OK;
-    icosa_points_kernel<<<nxb_grid_for(v_end - v_begin, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    icosa_points_kernel<<<nxb_grid_resident(icosa_points_kernel, 256, 0, ((v_end - v_begin) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(
         k, v_begin, v_end, (float4 *)xyz_f32, xyz_f64);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
@@ -164,7 +209,7 @@ NXB_API int nxb_mesh_icosa_cells(int k, int64_t t_begin, int64_t t_end, int32_t 
     int64_t T = 20 * (int64_t)k * k;
     NXB_ARG(0 <= t_begin && t_begin <= t_end && t_end <= T);
     if (t_end == t_begin) return NXB_OK;
-    icosa_cells_kernel<<<nxb_grid_for(t_end - t_begin, 256, 8), 256, 0, (cudaStream_t)stream>>>(k, t_begin, t_end, cells);
+    icosa_cells_kernel<<<nxb_grid_resident(icosa_cells_kernel, 256, 0, ((t_end - t_begin) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(k, t_begin, t_end, cells);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -181,7 +226,7 @@ NXB_API int nxb_xyz_f64_to_f32(const double *xyz_f64, int64_t n, double scale, n
     NXB_ARG(n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(xyz_f64 && xyz_f32);
-    xyz_f64_to_f32_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(xyz_f64, n, scale, (float4 *)xyz_f32);
+    xyz_f64_to_f32_kernel<<<nxb_grid_resident(xyz_f64_to_f32_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>(xyz_f64, n, scale, (float4 *)xyz_f32);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

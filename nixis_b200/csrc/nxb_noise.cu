@@ -1,5 +1,6 @@
 // OpenSimplex noise / fBm kernels and the table handle (C-ABI: include/nixis_b200.h).
 #include "nxb_noise.cuh"
+#include "nxb_noise3_fast.cuh"
 #ifdef NXB_HAVE_NOISE4
 #include "nxb_noise4.cuh"
 #else
@@ -100,7 +101,7 @@ NXB_API int nxb_noise3_f32(void *tables, const float *x, const float *y, const f
     NXB_ARG(tables && n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(x && y && z && out);
-    noise3_array_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, z, n, out);
+    noise3_array_kernel<<<nxb_grid_resident(noise3_array_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, z, n, out);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -110,7 +111,7 @@ NXB_API int nxb_noise2_f32(void *tables, const float *x, const float *y, int64_t
     NXB_ARG(tables && n >= 0);
     if (n == 0) return NXB_OK;
     NXB_ARG(x && y && out);
-    noise2_array_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, n, out);
+    noise2_array_kernel<<<nxb_grid_resident(noise2_array_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, n, out);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -124,7 +125,7 @@ NXB_API int nxb_noise4_f32(void *tables, const float *x, const float *y, const f
     nxb_set_error("noise4 not built");
     return NXB_ERR_UNSUPPORTED;
 #endif
-    noise4_array_kernel<<<nxb_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, z, w, n, out);
+    noise4_array_kernel<<<nxb_grid_resident(noise4_array_kernel, 256, 0, ((n) + 256 - 1) / 256), 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, x, y, z, w, n, out);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -169,6 +170,69 @@ fbm_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ xyz, in
     if (minmax) block_minmax_commit(lo, hi, minmax);
 }
 
+// ---- branch-free 3-D fBm (nxb_noise3_fast.cuh): one 1024-thread CTA per SM, 128.6 KB of
+// conflict-free tables in shared memory, persistent grid-stride over the vertices.
+struct FbmFastParams {
+    float freq[NXB_MAX_OCT];
+    float amp[NXB_MAX_OCT];     // 0.5 * amplitude / 103   (noise3d = v / 103, terrain.py:28)
+    float base;                 // sum of 0.5 * amplitude
+    int n_oct;
+};
+
+__global__ void __launch_bounds__(1024, 1)
+fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ xyz, int64_t n,
+                 const __grid_constant__ FbmFastParams prm, const float *__restrict__ init,
+                 float *__restrict__ out, float *__restrict__ minmax)
+{
+    extern __shared__ __align__(128) char nxf_sm[];
+    nxf_build_tables(tab->perm8, tab->grad8, nxf_sm, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = __ldg(xyz + v);
+        float acc = init ? init[v] : 0.0f;
+#pragma unroll 1
+        for (int o = 0; o < prm.n_oct; ++o) {
+            const float f = prm.freq[o];
+            acc = fmaf(nxf_noise3_x103(p.x * f, p.y * f, p.z * f, nxf_sm, lane4), prm.amp[o], acc);
+        }
+        acc += prm.base;
+        out[v] = acc;
+        lo = fminf(lo, acc);
+        hi = fmaxf(hi, acc);
+    }
+    if (minmax) block_minmax_commit(lo, hi, minmax);
+}
+
+static bool g_fbm_fast_attr[64] = {false};
+
+static int fbm3_fast_launch(void *tables, const nxb_float4 *xyz_unit, int64_t n, int cnt,
+                            const double *freq_host, const double *amp_host,
+                            const float *init, float *out, float *minmax, cudaStream_t st)
+{
+    FbmFastParams prm;
+    memset(&prm, 0, sizeof prm);
+    double base = 0.0;
+    for (int o = 0; o < cnt; ++o) {
+        prm.freq[o] = (float)freq_host[o];
+        prm.amp[o] = (float)(0.5 * amp_host[o] / 103.0);
+        base += 0.5 * amp_host[o];
+    }
+    prm.base = (float)base;
+    prm.n_oct = cnt;
+    int dev = 0;
+    NXB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !g_fbm_fast_attr[dev]) {
+        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NXF_SMEM_BYTES));
+        g_fbm_fast_attr[dev] = true;
+    }
+    int grid = nxb_grid_resident(fbm3_fast_kernel, 1024, NXF_SMEM_BYTES, (n + 1023) / 1024);
+    fbm3_fast_kernel<<<grid, 1024, NXF_SMEM_BYTES, st>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, init, out, minmax);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
 static int fbm_launch(int dim, void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
                       const double *freq_host, const double *amp_host, const double *w_host,
                       const float *init, float *out, float *minmax, void *stream)
@@ -189,7 +253,19 @@ static int fbm_launch(int dim, void *tables, const nxb_float4 *xyz_unit, int64_t
         }
         prm.n_oct = cnt;
         float *mm = (done + cnt >= n_oct) ? minmax : nullptr;
-        int grid = nxb_grid_for(n, 256, 8);
+        // the branch-free kernel floors with the magic-number trick: lattice coordinates must stay
+        // below 2^21 (unit-sphere positions: |x| + |stretch| <= 1.75 * freq)
+        double fmax = 0.0;
+        for (int o = 0; o < cnt; ++o) fmax = fabs(freq_host[done + o]) > fmax ? fabs(freq_host[done + o]) : fmax;
+        if (dim == 3 && cnt > 0 && fmax * 1.75 < (double)NXF_MAX_COORD && !getenv("NXB_FBM_V1")) {
+            int rc = fbm3_fast_launch(tables, xyz_unit, n, cnt, freq_host + done, amp_host + done, cur_init, out, mm, (cudaStream_t)stream);
+            if (rc) return rc;
+            done += cnt;
+            cur_init = out;
+            continue;
+        }
+        int grid = dim == 3 ? nxb_grid_resident(fbm_kernel<3>, 256, 0, (n + 255) / 256)
+                            : nxb_grid_resident(fbm_kernel<4>, 256, 0, (n + 255) / 256);
         if (dim == 3)
             fbm_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, cur_init, out, mm);
         else

@@ -1,0 +1,263 @@
+// Branch-free OpenSimplex 3-D evaluation for the fused fBm kernel (sm_100a).
+//
+// Same candidate set as the reference (opensimplex.py:266-759) -- the legacy algorithm is not a
+// full lattice sum, so the SAME comparisons must pick the SAME lattice points -- but organised so
+// that every lane of a warp executes the same instruction stream whatever region of the lattice
+// cell it falls in (profiles/r01_ncu_summary.json: the branchy version ran at 16.4 of 32 active
+// lanes and 706 warp-instructions per evaluation):
+//
+//   * the 8 corners of the lattice cube are ALWAYS evaluated; a per-lane constant T (2 or -16)
+//     replaces the "2" in attn = 2 - |d|^2, so a corner the reference would not visit gets a
+//     negative attn and contributes exactly 0.  Which corners are live: the region's simplex
+//     corners plus, when an "extra" lattice point of the reference happens to be a cube corner,
+//     that corner.
+//   * at most two extras are NOT cube corners (offsets containing -1 or 2).  They come from a
+//     19-entry table of displacement constants / hash offsets indexed by a small per-lane code.
+//   * only the ~25-instruction selection logic branches on the region (three short warp-level
+//     branches; coherent warps execute one of them).
+//   * hash and gradient tables live in shared memory in a bank-conflict-free layout: entry e of
+//     lane l sits at word e*32 + l, so every lookup is one wavefront whatever the indices are.
+//     Values of the permutation table are stored pre-multiplied by the row pitch (128 B), the
+//     last hash level indexes three float tables holding the gradient components directly
+//     (GRADIENTS_3D[perm_grad_index_3D[h]], opensimplex.py:123-130): no decode arithmetic.
+//   * floor() uses the 1.5*2^23 magic-number trick (exact for |x| < 2^22), no F2I/I2F.
+//
+// This header is plain C++ apart from a few intrinsics so that tools/host_noise_check.cpp can
+// compile it with g++ and compare against the float64 oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#include <math.h>
+#include <string.h>
+#define NXF_DEV inline
+static inline float nxf_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t nxf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#define nxf_fma(a, b, c) fmaf(a, b, c)
+#else
+#define NXF_DEV __device__ __forceinline__
+#define nxf_as_float(u) __uint_as_float(u)
+#define nxf_as_uint(f) __float_as_uint(f)
+#define nxf_fma(a, b, c) fmaf(a, b, c)
+#endif
+
+#define NXF_ROW 128u                    // bytes per table row (32 lanes x 4 B)
+#define NXF_MASK 0x7F80u                // (e & 255) * 128
+#define NXF_TAB_BYTES (256u * NXF_ROW)  // one replicated 256-entry table: 32 KB
+#define NXF_OFF_P 0u
+#define NXF_OFF_GX (1u * NXF_TAB_BYTES)
+#define NXF_OFF_GY (2u * NXF_TAB_BYTES)
+#define NXF_OFF_GZ (3u * NXF_TAB_BYTES)
+#define NXF_OFF_EXT (4u * NXF_TAB_BYTES)        // 19 extra records x 32 B (not replicated)
+#define NXF_SMEM_BYTES (NXF_OFF_EXT + 32u * 20u)
+#define NXF_MAX_COORD 2000000.0f        // |lattice coordinate| bound for the magic-number floor
+
+// record of one non-cube extra lattice point: displacement constants (offset + m/3), the live
+// constant T (2, or -16 for "no extra"), hash offsets pre-multiplied by the row pitch
+struct NxfExtra { float cx, cy, cz, T; int32_t ox, oy, oz, pad; };
+
+// offsets of the 18 non-cube extras, in the order the selection logic indexes them
+//  0..5   tet(0,0,0), (0,0,0) among the two closest: axis k -> 2k, 2k+1     (opensimplex.py:321-350)
+//  6..11  tet(1,1,1), (1,1,1) among the two closest: pair p -> 6+2p, 7+2p   (opensimplex.py:436-466)
+//  12..14 (1,1,1) - 2 e_k                                                   (m = 1)
+//  15..17 2 e_k                                                             (m = 2)
+//  18     none
+#ifdef __CUDACC__
+__device__
+#endif
+static const int8_t NXF_EXTRA_OFFSETS[19][3] = {
+    {1, -1, 0}, {1, 0, -1}, {-1, 1, 0}, {0, 1, -1}, {-1, 0, 1}, {0, -1, 1},
+    {2, 1, 0}, {1, 2, 0}, {2, 0, 1}, {1, 0, 2}, {0, 2, 1}, {0, 1, 2},
+    {-1, 1, 1}, {1, -1, 1}, {1, 1, -1},
+    {2, 0, 0}, {0, 2, 0}, {0, 0, 2},
+    {0, 0, 0}};
+
+struct NxfCtx {
+    const char *sm;         // shared-memory base of the tables
+    uint32_t lane4;         // lane * 4
+    uint32_t xb7, yb7, zb7; // (lattice base & 255) * 128, unmasked
+    float dx0, dy0, dz0;
+    float v;
+};
+
+NXF_DEV uint32_t nxf_ldu(const NxfCtx &c, uint32_t off, uint32_t idx)
+{
+    return *reinterpret_cast<const uint32_t *>(c.sm + off + idx);
+}
+NXF_DEV float nxf_ldf(const NxfCtx &c, uint32_t off, uint32_t idx)
+{
+    return *reinterpret_cast<const float *>(c.sm + off + idx);
+}
+// one hash level: row ((h + add) & 255) of the P table, this lane's copy
+NXF_DEV uint32_t nxf_hash(const NxfCtx &c, uint32_t h_plus_add)
+{
+    return nxf_ldu(c, NXF_OFF_P, (h_plus_add & NXF_MASK) | c.lane4);
+}
+
+// contribution of the lattice point whose last-level table index is idx (bytes) and whose
+// displacement is (dx,dy,dz); T is 2 for a live point, -16 for a dead one
+NXF_DEV void nxf_contrib(NxfCtx &c, uint32_t idx, float dx, float dy, float dz, float T)
+{
+    float at = nxf_fma(-dz, dz, nxf_fma(-dy, dy, nxf_fma(-dx, dx, T)));
+    at = fmaxf(at, 0.0f);
+    const float gx = nxf_ldf(c, NXF_OFF_GX, idx), gy = nxf_ldf(c, NXF_OFF_GY, idx), gz = nxf_ldf(c, NXF_OFF_GZ, idx);
+    const float dot = nxf_fma(gz, dz, nxf_fma(gy, dy, gx * dx));
+    at *= at;
+    c.v = nxf_fma(at * at, dot, c.v);
+}
+
+template <int I, int J, int K>
+NXF_DEV void nxf_corner(NxfCtx &c, uint32_t hxy, float T)
+{
+    constexpr float m3 = (float)(I + J + K) * (1.0f / 3.0f);
+    const uint32_t idx = ((hxy + c.zb7 + (uint32_t)K * NXF_ROW) & NXF_MASK) | c.lane4;
+    nxf_contrib(c, idx, c.dx0 - ((float)I + m3), c.dy0 - ((float)J + m3), c.dz0 - ((float)K + m3), T);
+}
+
+NXF_DEV void nxf_extra(NxfCtx &c, int e)
+{
+    const NxfExtra &r = *reinterpret_cast<const NxfExtra *>(c.sm + NXF_OFF_EXT + (uint32_t)e * 32u);
+    uint32_t h = nxf_hash(c, c.xb7 + (uint32_t)r.ox);
+    h = nxf_hash(c, h + c.yb7 + (uint32_t)r.oy);
+    const uint32_t idx = ((h + c.zb7 + (uint32_t)r.oz) & NXF_MASK) | c.lane4;
+    nxf_contrib(c, idx, c.dx0 - r.cx, c.dy0 - r.cy, c.dz0 - r.cz, r.T);
+}
+
+// opensimplex.py:306-312 / 421-427 / 584-599: keep the two best of three candidates.
+// Starts with a = cand0, b = cand1; cand2 replaces the worse of them if it beats it.
+// "better" = larger score.  Tie rules are the reference's (>= on a vs b, strict on the newcomer).
+NXF_DEV void nxf_pick2(float s0, float s1, float s2, int c0, int c1, int c2, int &ap, float &as, int &bp, float &bs)
+{
+    ap = c0; as = s0; bp = c1; bs = s1;
+    if (as >= bs && s2 > bs) { bs = s2; bp = c2; }
+    else if (as < bs && s2 > as) { as = s2; ap = c2; }
+}
+
+// x,y,z: lattice-space coordinates (vertex * octave frequency).  Returns noise3d * 103.
+NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_t lane4)
+{
+    const float MAGIC = 12582912.0f;   // 1.5 * 2^23: (x + MAGIC) - MAGIC rounds to nearest integer
+    const float so = (x + y + z) * (-1.0f / 6.0f);
+    const float xs = x + so, ys = y + so, zs = z + so;
+    const float tx = xs + MAGIC, ty = ys + MAGIC, tz = zs + MAGIC;
+    float bx = tx - MAGIC, by = ty - MAGIC, bz = tz - MAGIC;
+    // floor = round-to-nearest, minus 1 where that rounded up (opensimplex.py:18-21)
+    const bool ux = bx > xs, uy = by > ys, uz = bz > zs;
+    bx = ux ? bx - 1.0f : bx; by = uy ? by - 1.0f : by; bz = uz ? bz - 1.0f : bz;
+    NxfCtx c;
+    c.sm = sm; c.lane4 = lane4;
+    // low mantissa bits of (x + MAGIC) are the integer; only bits 0..7 survive the masks
+    c.xb7 = (nxf_as_uint(tx) - (ux ? 1u : 0u)) << 7;
+    c.yb7 = (nxf_as_uint(ty) - (uy ? 1u : 0u)) << 7;
+    c.zb7 = (nxf_as_uint(tz) - (uz ? 1u : 0u)) << 7;
+    const float fx = xs - bx, fy = ys - by, fz = zs - bz;
+    const float fsum = fx + fy + fz;
+    // position relative to the cell origin: f + fsum/3 (the un-skew of the in-cell coordinates;
+    // the reference's x - xb, opensimplex.py:283-297, is the same quantity)
+    c.dx0 = nxf_fma(fsum, 1.0f / 3.0f, fx);
+    c.dy0 = nxf_fma(fsum, 1.0f / 3.0f, fy);
+    c.dz0 = nxf_fma(fsum, 1.0f / 3.0f, fz);
+    c.v = 0.0f;
+
+    // ---- selection: live constants of the 8 cube corners + two extra codes ------------------
+    const float LIVE = 2.0f, DEAD = -16.0f;
+    float T000, T100, T010, T001, T110, T101, T011, T111;
+    int e0, e1 = 18;
+    if (fsum <= 1.0f) {                                    // tetrahedron at (0,0,0)
+        int ap, bp; float as, bs;
+        nxf_pick2(fx, fy, fz, 1, 2, 4, ap, as, bp, bs);
+        const float w = 1.0f - fsum;
+        T000 = T100 = T010 = T001 = LIVE; T111 = DEAD;
+        if (w > as || w > bs) {
+            const int cc = (bs > as) ? bp : ap;            // 1, 2 or 4
+            e0 = (cc >> 1) * 2; e1 = e0 + 1;
+            T110 = T101 = T011 = DEAD;
+        } else {
+            const int cc = ap | bp;                        // 3, 5 or 6: that cube corner is the first extra
+            e0 = 12 + ((6 - cc + 1) >> 1);                 // (1,1,1) - 2 e_k, k = the axis not in cc... see table
+            T110 = cc == 3 ? LIVE : DEAD; T101 = cc == 5 ? LIVE : DEAD; T011 = cc == 6 ? LIVE : DEAD;
+        }
+    } else if (fsum >= 2.0f) {                             // tetrahedron at (1,1,1)
+        int ap, bp; float as, bs;
+        nxf_pick2(-fx, -fy, -fz, 6, 5, 3, ap, as, bp, bs); // two SMALLEST of fx,fy,fz
+        const float w = fsum - 3.0f;                       // -(3 - fsum), same sign convention as the scores
+        T110 = T101 = T011 = T111 = LIVE; T000 = DEAD;
+        if (w > as || w > bs) {
+            const int cc = (bs > as) ? bp : ap;            // 3, 5 or 6
+            e0 = 6 + (cc >> 1 == 1 ? 0 : (cc == 5 ? 2 : 4)); e1 = e0 + 1;
+            T100 = T010 = T001 = DEAD;
+        } else {
+            const int cc = ap & bp;                        // 1, 2 or 4
+            e0 = 15 + (cc >> 1);
+            T100 = cc == 1 ? LIVE : DEAD; T010 = cc == 2 ? LIVE : DEAD; T001 = cc == 4 ? LIVE : DEAD;
+        }
+    } else {                                               // octahedron
+        const float p1 = fx + fy, p2 = fx + fz, p3 = fy + fz;
+        const bool f1 = p1 > 1.0f, f2 = p2 > 1.0f, f3 = p3 > 1.0f;
+        float as = f1 ? p1 - 1.0f : 1.0f - p1;  int ap = f1 ? 3 : 4;  bool afar = f1;
+        float bs = f2 ? p2 - 1.0f : 1.0f - p2;  int bp = f2 ? 5 : 2;  bool bfar = f2;
+        const float sc = f3 ? p3 - 1.0f : 1.0f - p3;  const int cp = f3 ? 6 : 1;
+        if (as <= bs && as < sc) { ap = cp; afar = f3; }
+        else if (as > bs && bs < sc) { bp = cp; bfar = f3; }
+        T100 = T010 = T001 = T110 = T101 = T011 = LIVE;
+        T000 = T111 = DEAD;
+        if (afar == bfar) {
+            if (afar) {                                    // (1,1,1) + 2 e_k on the shared axis
+                const int cc = ap & bp;
+                T111 = LIVE;
+                e0 = 15 + ((cc & 1) ? 0 : ((cc & 2) ? 1 : 2));
+            } else {                                       // (0,0,0) + (1,1,1) - 2 e_k on the omitted axis
+                const int cc = ap | bp;
+                T000 = LIVE;
+                e0 = 12 + (!(cc & 1) ? 0 : (!(cc & 2) ? 1 : 2));
+            }
+        } else {
+            const int c1 = afar ? ap : bp, c2 = afar ? bp : ap;
+            e0 = 12 + (!(c1 & 1) ? 0 : (!(c1 & 2) ? 1 : 2));
+            e1 = 15 + ((c2 & 1) ? 0 : ((c2 & 2) ? 1 : 2));
+        }
+    }
+
+    // ---- the 8 cube corners: shared hash tree (2 + 4 lookups), then one leaf each -----------
+    const uint32_t hx0 = nxf_hash(c, c.xb7), hx1 = nxf_hash(c, c.xb7 + NXF_ROW);
+    const uint32_t h00 = nxf_hash(c, hx0 + c.yb7), h01 = nxf_hash(c, hx0 + c.yb7 + NXF_ROW);
+    const uint32_t h10 = nxf_hash(c, hx1 + c.yb7), h11 = nxf_hash(c, hx1 + c.yb7 + NXF_ROW);
+    nxf_corner<0, 0, 0>(c, h00, T000);
+    nxf_corner<1, 0, 0>(c, h10, T100);
+    nxf_corner<0, 1, 0>(c, h01, T010);
+    nxf_corner<0, 0, 1>(c, h00, T001);
+    nxf_corner<1, 1, 0>(c, h11, T110);
+    nxf_corner<1, 0, 1>(c, h10, T101);
+    nxf_corner<0, 1, 1>(c, h01, T011);
+    nxf_corner<1, 1, 1>(c, h11, T111);
+    nxf_extra(c, e0);
+    nxf_extra(c, e1);
+    return c.v;
+}
+
+// Fill the replicated tables.  perm8 / grad8 as in NxbTables (nxb_noise.cuh).  Called by every
+// thread of the CTA (tid, nthreads); on the host with (0, 1).
+NXF_DEV void nxf_build_tables(const uint8_t *perm8, const uint8_t *grad8, char *sm, int tid, int nthreads)
+{
+    uint32_t *P = reinterpret_cast<uint32_t *>(sm + NXF_OFF_P);
+    float *GX = reinterpret_cast<float *>(sm + NXF_OFF_GX);
+    float *GY = reinterpret_cast<float *>(sm + NXF_OFF_GY);
+    float *GZ = reinterpret_cast<float *>(sm + NXF_OFF_GZ);
+    for (int w = tid; w < 256 * 32; w += nthreads) {
+        const int e = w >> 5;
+        const uint32_t g = grad8[e], ax = g >> 3;
+        P[w] = (uint32_t)perm8[e] << 7;
+        GX[w] = ((g & 1) ? -1.0f : 1.0f) * (ax == 0 ? 11.0f : 4.0f);
+        GY[w] = ((g & 2) ? -1.0f : 1.0f) * (ax == 1 ? 11.0f : 4.0f);
+        GZ[w] = ((g & 4) ? -1.0f : 1.0f) * (ax == 2 ? 11.0f : 4.0f);
+    }
+    NxfExtra *rec = reinterpret_cast<NxfExtra *>(sm + NXF_OFF_EXT);
+    for (int e = tid; e < 19; e += nthreads) {
+        const int8_t *o = NXF_EXTRA_OFFSETS[e];
+        const float cc = (float)(o[0] + o[1] + o[2]) * (1.0f / 3.0f);
+        rec[e].cx = (float)o[0] + cc; rec[e].cy = (float)o[1] + cc; rec[e].cz = (float)o[2] + cc;
+        rec[e].T = e == 18 ? -16.0f : 2.0f;
+        rec[e].ox = o[0] * (int)NXF_ROW; rec[e].oy = o[1] * (int)NXF_ROW; rec[e].oz = o[2] * (int)NXF_ROW;
+        rec[e].pad = 0;
+    }
+}

@@ -18,37 +18,48 @@ from .util import DeviceMesh
 RAIN_AMOUNT = 0.3 / 320         # erosion.py:182
 
 
-def _positions(nodes):
-    """-> (float32 [V,4] positions / scale, scale).  Distances are scale * |delta|."""
-    if isinstance(nodes, DeviceMesh):
-        return nodes.xyz, nodes.radius
-    if isinstance(nodes, torch.Tensor):
-        return nodes, 1.0
-    v = np.ascontiguousarray(nodes, dtype=np.float64)
-    scale = float(np.abs(v[: min(len(v), 4096)]).max()) or 1.0
-    return rt.xyz_from_f64(rt.upload(v), 1.0 / scale), scale
-
-
 def _neighbors(neighbors):
     if isinstance(neighbors, torch.Tensor):
         return neighbors
     return rt.upload(np.ascontiguousarray(neighbors, dtype=np.int32))
 
 
-class Erosion3State:
-    """Device-resident state of erode_terrain3: (h, water, sediment) x ping-pong."""
+def _edge_lengths(nodes, adj):
+    """FP32 edge length of every adjacency slot, computed once in FP64 on the device
+    (erosion.py:34-40, 227-229: distances between the undisplaced sphere positions)."""
+    if isinstance(nodes, DeviceMesh):
+        return rt.icosa_edge_lengths(nodes.k, adj, nodes.v_begin, nodes.v_begin + adj.shape[0], nodes.radius)
+    if isinstance(nodes, torch.Tensor):
+        n64 = nodes[:, :3].to(torch.float64).contiguous()
+        return rt.edge_lengths(n64, adj)
+    v = np.ascontiguousarray(nodes, dtype=np.float64)
+    return rt.edge_lengths(rt.upload(v), adj)
 
-    def __init__(self, xyz, scale, adj, heights32):
-        self.xyz, self.scale, self.adj = xyz, float(scale), adj
-        n = heights32.numel()
-        self.cur = (heights32, torch.zeros(n, dtype=rt.F32, device=heights32.device),
-                    torch.zeros(n, dtype=rt.F32, device=heights32.device))
-        self.nxt = tuple(torch.empty_like(t) for t in self.cur)
+
+class Erosion3State:
+    """Device-resident state of erode_terrain3: tile plan, edge lengths, (h, water, sediment) x ping-pong.
+    Buffers are padded to a whole number of 256-vertex tiles."""
+
+    def __init__(self, nodes, adj, heights32, plan=None, dist=None):
+        self.adj = adj
+        self.n = adj.shape[0]
+        self.plan = plan if plan is not None else rt.ErosionPlan(adj)
+        self.dist = dist if dist is not None else _edge_lengths(nodes, adj)
+        cap, dev = self.plan.capacity, adj.device
+        h = torch.zeros(cap, dtype=rt.F32, device=dev)
+        h[: self.n].copy_(heights32[: self.n])
+        self.cur = (h, torch.zeros(cap, dtype=rt.F32, device=dev), torch.zeros(cap, dtype=rt.F32, device=dev))
+        self.nxt = tuple(torch.zeros(cap, dtype=rt.F32, device=dev) for _ in range(3))
+        self.iterations = 0
+
+    def reset(self, heights32):
+        self.cur[0][: self.n].copy_(heights32[: self.n])
+        self.cur[1].zero_()
+        self.cur[2].zero_()
         self.iterations = 0
 
     def step(self, rain=RAIN_AMOUNT):
-        n = self.cur[0].numel()
-        rt.erode3_step(self.xyz, self.adj, self.cur, self.nxt, 0, n, rain, self.scale)
+        rt.erode3_step(self.plan, self.dist, self.cur, self.nxt, rain)
         self.cur, self.nxt = self.nxt, self.cur
         self.iterations += 1
 
@@ -58,16 +69,16 @@ class Erosion3State:
 
     @property
     def heights(self):
-        return self.cur[0]
+        return self.cur[0][: self.n]
 
     @property
     def water(self):
         """Water AFTER the last sweep (the reference's `water` array at that point)."""
-        return self.cur[1]
+        return self.cur[1][: self.n]
 
     @property
     def sediment(self):
-        return self.cur[2]
+        return self.cur[2][: self.n]
 
 
 def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbose=True, return_state=False):
@@ -81,34 +92,33 @@ def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbos
         print("Starting terrain erosion...")
     if num_iter <= 0:
         num_iter = 1
-    xyz, scale = _positions(nodes)
     adj = _neighbors(neighbors)
     dev_io = isinstance(heights, torch.Tensor)
-    h32 = heights.clone() if dev_io else rt.upload_f32(heights)
-    st = Erosion3State(xyz, scale, adj, h32)
+    h32 = heights if dev_io else rt.upload_f32(heights)
+    st = Erosion3State(nodes, adj, h32)
     for i in range(num_iter):
         if verbose:
             print("  Erosion pass:", i + 1, "of", num_iter)
         st.step()
     if dev_io:
         return st if return_state else st.heights
-    rt.download_f64(st.heights, out=heights)
+    rt.download_f64(st.heights.contiguous(), out=heights)
     if return_state:
-        return rt.download_f64(st.water), rt.download_f64(st.sediment)
+        return rt.download_f64(st.water.contiguous()), rt.download_f64(st.sediment.contiguous())
     return None
 
 
 def erosion_iteration3(verts, neighbors, r_buff, wat, sed):
     """One sweep (erosion.py:197-279): r_buff, wat, sed (numpy float64) are updated in place.
     `wat` must already contain this iteration's rain, as in erode_terrain3."""
-    xyz, scale = _positions(verts)
     adj = _neighbors(neighbors)
-    src = (rt.upload_f32(r_buff), rt.upload_f32(wat), rt.upload_f32(sed))
-    dst = tuple(torch.empty_like(t) for t in src)
-    rt.erode3_step(xyz, adj, src, dst, 0, src[0].numel(), 0.0, scale)
-    rt.download_f64(dst[0], out=r_buff)
-    rt.download_f64(dst[1], out=wat)
-    rt.download_f64(dst[2], out=sed)
+    st = Erosion3State(verts, adj, rt.upload_f32(r_buff))
+    st.cur[1][: st.n].copy_(rt.upload_f32(wat))
+    st.cur[2][: st.n].copy_(rt.upload_f32(sed))
+    st.step(rain=0.0)
+    rt.download_f64(st.heights.contiguous(), out=r_buff)
+    rt.download_f64(st.water.contiguous(), out=wat)
+    rt.download_f64(st.sediment.contiguous(), out=sed)
 
 
 def erosion_iteration1(neighbors, r_buff, w_buff):

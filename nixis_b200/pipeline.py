@@ -111,5 +111,9 @@ class TerrainPipeline:
         return assemble_heights(h, mm=mm)
 
     def erosion_state(self, heights32):
-        from .erosion import Erosion3State
-        return Erosion3State(self.mesh.xyz, self.radius, self.adj, heights32)
+        """Plan + edge lengths are built once per mesh and reused by every state."""
+        from .erosion import Erosion3State, _edge_lengths
+        if getattr(self, "_plan", None) is None:
+            self._plan = rt.ErosionPlan(self.adj)
+            self._dist = _edge_lengths(self.mesh, self.adj)
+        return Erosion3State(self.mesh, self.adj, heights32, plan=self._plan, dist=self._dist)

@@ -233,10 +233,49 @@ def adj_sort(adj):
     return out
 
 
-def erode3_step(xyz, adj, src, dst, v_begin, v_end, rain, radius):
-    """src/dst: (h, w, s) tuples of float32 CUDA vectors."""
-    _lib.call("nxb_erode3_step_f32", _ptr(xyz), _ptr(adj), _ptr(src[0]), _ptr(src[1]), _ptr(src[2]),
-              _ptr(dst[0]), _ptr(dst[1]), _ptr(dst[2]), v_begin, v_end, C.c_float(rain), C.c_float(radius), _stream())
+ERO_TILE = 256
+
+
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def edge_lengths(nodes64, adj, n_own=None):
+    """float64 [.,3] CUDA positions + int32 [n_own,6] table -> float32 [round_up(n_own,256)*6] edge lengths."""
+    n_own = adj.shape[0] if n_own is None else n_own
+    dist = torch.zeros(round_up(n_own, ERO_TILE) * 6, dtype=F32, device=adj.device)
+    _lib.call("nxb_edge_lengths_f64", _ptr(nodes64), _ptr(adj), n_own, _ptr(dist), _stream())
+    return dist
+
+
+def icosa_edge_lengths(k, adj_rows, v_begin, v_end, radius):
+    """Edge lengths of the closed-form icosphere for rows [v_begin, v_end) (global ids in adj_rows)."""
+    n = v_end - v_begin
+    dist = torch.zeros(round_up(n, ERO_TILE) * 6, dtype=F32, device=adj_rows.device)
+    _lib.call("nxb_mesh_icosa_edge_lengths", int(k), _ptr(adj_rows), v_begin, v_end, C.c_double(radius), _ptr(dist), _stream())
+    return dist
+
+
+class ErosionPlan:
+    """Tile plan (halo segments + 16-bit tile-local adjacency) of an int32 [n_own,6] neighbour table
+    whose indices address buffers of `capacity` elements."""
+
+    def __init__(self, adj, capacity=None):
+        self.adj = adj
+        self.n_own = adj.shape[0]
+        self.capacity = round_up(self.n_own, ERO_TILE) if capacity is None else int(capacity)
+        nbytes = _lib.load().nxb_erode_plan_bytes(self.n_own)
+        self.mem = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=adj.device)
+        stats = (C.c_int32 * 3)()
+        _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
+        self.n_tiles, self.n_irregular, self.max_halo = stats[0], stats[1], stats[2]
+
+
+def erode3_step(plan, dist, src, dst, rain):
+    """src/dst: (h, w, s) tuples of float32 CUDA vectors of plan.capacity elements."""
+    _lib.call("nxb_erode3_plan_step_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist),
+              _ptr(src[0]), _ptr(src[1]), _ptr(src[2]), _ptr(dst[0]), _ptr(dst[1]), _ptr(dst[2]),
+              plan.n_own, C.c_float(rain), _stream())
 
 
 def erode1_step(adj, h_in, h_out, v_begin, v_end):

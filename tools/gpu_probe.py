@@ -57,7 +57,8 @@ for k in (1000, 2500):
     h, _, _ = pipe.heights()
     best, avg = timeit(lambda: assemble_heights(pipe.fbm(out=out)), n=3, warm=1)
     print(f"k={k} fbm+assembly: {best:.3f} ms; mesh+adjacency build {t_mesh*1e3:.1f} ms")
-    st = pipe.erosion_state(h.clone())
+    t0 = time.perf_counter(); st = pipe.erosion_state(h.clone()); torch.cuda.synchronize()
+    print(f"k={k} erosion plan: {time.perf_counter()-t0:.3f}s tiles {st.plan.n_tiles} irregular {st.plan.n_irregular} max_halo {st.plan.max_halo}")
     best, avg = timeit(lambda: st.step(), n=20, warm=3)
     print(f"k={k} erode3 step: best {best:.4f} ms avg {avg:.4f} -> {V/best/1e3:.1f} Mvert-iter/s, {60*V/best/1e6:.1f} GB/s(alg)")
     a = st.cur[0]; b = torch.empty_like(a)

@@ -1,0 +1,60 @@
+// Host-side check of the FP32 branch-free noise core against the float64 oracle (no GPU needed).
+//   g++ -O2 -mfma -I. tools/host_noise_check.cpp oracle/libnixis_oracle.so -o /tmp/host_noise_check
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <random>
+#include "../nixis_b200/csrc/nxb_noise3_fast.cuh"
+extern "C" {
+void nxo_init(int64_t seed, int32_t *perm, int32_t *pgi);
+double nxo_noise3(double x, double y, double z, const int32_t *perm, const int32_t *pgi);
+}
+int main(int argc, char **argv)
+{
+    int64_t seed = argc > 1 ? atoll(argv[1]) : 12345;
+    int32_t perm[256], pgi[256];
+    nxo_init(seed, perm, pgi);
+    uint8_t perm8[256], grad8[256];
+    for (int i = 0; i < 256; ++i) {
+        perm8[i] = (uint8_t)perm[i];
+        int g = pgi[i] / 3, q = g / 3, a = g % 3;
+        grad8[i] = (uint8_t)(((q & 1) ? 0 : 1) | ((q & 2) ? 2 : 0) | ((q & 4) ? 4 : 0) | (a << 3));
+    }
+    std::vector<char> sm(NXF_SMEM_BYTES);
+    nxf_build_tables(perm8, grad8, sm.data(), 0, 1);
+    std::mt19937_64 rng(7);
+    std::uniform_real_distribution<double> U(-1, 1);
+    const double scales[] = {1.5, 9.4, 58.6, 366.2, 915.5, 5722.0, 35763.0};
+    for (double f : scales) {
+        double maxerr = 0, sumerr = 0; int nbig = 0; const int N = 400000;
+        double worst[3] = {0, 0, 0};
+        for (int i = 0; i < N; ++i) {
+            double x = U(rng), y = U(rng), z = U(rng);
+            double n = std::sqrt(x * x + y * y + z * z); x /= n; y /= n; z /= n;
+            float xf = (float)x, yf = (float)y, zf = (float)z, ff = (float)f;
+            uint32_t lane4 = (uint32_t)(i & 31) * 4;
+            float got = nxf_noise3_x103(xf * ff, yf * ff, zf * ff, sm.data(), lane4) * (1.0f / 103.0f);
+            // reference on the SAME float inputs (isolates arithmetic error from input rounding)
+            double ref = nxo_noise3((double)xf * (double)ff, (double)yf * (double)ff, (double)zf * (double)ff, perm, pgi);
+            double e = std::fabs((double)got - ref);
+            sumerr += e;
+            if (e > maxerr) { maxerr = e; worst[0] = x * f; worst[1] = y * f; worst[2] = z * f; }
+            if (e > 2e-5) ++nbig;
+        }
+        printf("f=%9.1f  max %.3e  mean %.3e  n(>2e-5) %d  worst at (%.4f %.4f %.4f)\n", f, maxerr, sumerr / N, nbig, worst[0], worst[1], worst[2]);
+    }
+    // lattice-aligned and tie-prone points
+    double maxerr = 0; int n = 0, nflip = 0;
+    for (int a = -8; a <= 8; ++a) for (int b = -8; b <= 8; ++b) for (int c = -8; c <= 8; ++c) {
+        float x = a * 0.25f + 0.001f * (a % 3), y = b * 0.25f, z = c * 0.25f - 0.002f * (c % 2);
+        float got = nxf_noise3_x103(x, y, z, sm.data(), (uint32_t)(n & 31) * 4) * (1.0f / 103.0f);
+        double ref = nxo_noise3(x, y, z, perm, pgi);
+        double e = std::fabs(got - ref);
+        if (e > maxerr) maxerr = e;
+        if (e > 2e-5) ++nflip;
+        ++n;
+    }
+    printf("quarter-lattice points: n=%d max %.3e n(>2e-5) %d\n", n, maxerr, nflip);
+    return 0;
+}
