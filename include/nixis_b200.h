@@ -151,6 +151,20 @@ int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const flo
 /* erosion.py:76-99 erosion_iteration1 */
 int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
                         int64_t v_begin, int64_t v_end, void *stream);
+/* ---- multi-GPU halo exchange over NVLink peer memory (csrc/nxb_halo.cu) ------------------------
+ * After a sweep, store this rank's boundary h / w values straight into every peer's halo slots
+ * (peer_h[p] / peer_w[p] are the peer's state buffers mapped into this process, e.g. by
+ * torch.distributed._symmetric_memory) and raise flag_value in the peer's flag slot for this rank.
+ * send_idx: concatenated LOCAL indices, peer after peer (src_begin / count per peer); dst_off[p] =
+ * first element of peer p's buffer this rank fills.  ticket: device uint32, zero.  One fused kernel. */
+int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send_idx, int npeers,
+                     void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+                     const int64_t *dst_off, const int64_t *src_begin, const int64_t *count,
+                     uint32_t flag_value, void *ticket, void *stream);
+/* Stream-ordered wait until flags[src_ranks[i]] >= target for all i (flags: this rank's uint32 array,
+ * written by the peers' nxb_halo_put_f32; src_ranks: device int32[npeers]). */
+int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, void *stream);
+
 /* gather / scatter of halo values for the multi-GPU exchange: dst[i] = src[idx[i]] and
  * dst[idx[i]] = src[i] */
 int nxb_gather_f32(const float *src, const int32_t *idx, int64_t n, float *dst, void *stream);

@@ -1,0 +1,113 @@
+// Per-sweep halo exchange of the sharded erosion stencil over NVLink peer memory.
+//
+// The stencil has radius 1 and reads only neighbours' height and water (erosion.py:225-247), so
+// after every sweep a rank owes each peer the h / w values of the own vertices that peer's rows
+// reference.  The peer's halo slots for this rank are ONE contiguous range (partition.py), so the
+// exchange is: gather own[send_idx[i]] and store it straight into the peer's state buffer through
+// its NVLink-mapped address -- pack and transfer are one kernel, there is no staging buffer, no
+// NCCL call and no host involvement.  Completion is signalled with a per-source flag in the peer's
+// memory (release at system scope after every block has fenced); the next sweep is preceded by a
+// one-warp kernel that spins until the flags of all peers reach the expected sweep number.
+//
+// Message sizes are 10^4..10^5 vertices x 8 B per peer: latency, not bandwidth, is what matters,
+// which is why this avoids per-peer launches (one fused kernel for all peers).
+#include "nxb_common.cuh"
+
+#define HALO_MAX_PEERS 8
+
+struct HaloPeer {
+    float *h, *w;               // peer's destination buffers (NVLink-mapped), already offset to its halo area
+    uint32_t *flag;             // peer's flag slot for THIS rank
+    int64_t dst_off;            // first halo slot (relative to h / w) this rank fills
+    int64_t src_begin;          // offset of this peer's list inside the concatenated send list
+    int64_t count;
+};
+
+struct HaloPutArgs {
+    const float *h, *w;         // this rank's freshly written buffers
+    const int32_t *send_idx;    // concatenated local indices, peer after peer
+    HaloPeer peer[HALO_MAX_PEERS];
+    int npeers;
+    int64_t total;
+    uint32_t flag_value;
+    unsigned int *ticket;       // device counter for the last-block pattern (zero between launches)
+};
+
+__global__ void __launch_bounds__(256)
+halo_put_kernel(const __grid_constant__ HaloPutArgs a)
+{
+    __shared__ bool s_last;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = 0;
+#pragma unroll
+        for (int q = 1; q < HALO_MAX_PEERS; ++q) if (q < a.npeers && i >= a.peer[q].src_begin) p = q;
+        const int64_t j = i - a.peer[p].src_begin;
+        const int32_t v = __ldg(a.send_idx + i);
+        a.peer[p].h[a.peer[p].dst_off + j] = a.h[v];
+        a.peer[p].w[a.peer[p].dst_off + j] = a.w[v];
+    }
+    __threadfence_system();                 // this thread's peer stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < a.npeers) {  // ... before the last block raises the flags
+        __threadfence_system();
+        volatile uint32_t *f = a.peer[threadIdx.x].flag;
+        *f = a.flag_value;
+        __threadfence_system();
+    }
+    if (s_last && threadIdx.x == 0) *a.ticket = 0;
+}
+
+// peers_dev: array of npeers structs in host memory (copied by value into the launch)
+NXB_API int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send_idx, int npeers,
+                             void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+                             const int64_t *dst_off, const int64_t *src_begin, const int64_t *count,
+                             uint32_t flag_value, void *ticket, void *stream)
+{
+    NXB_ARG(npeers >= 0 && npeers <= HALO_MAX_PEERS);
+    if (npeers == 0) return NXB_OK;
+    NXB_ARG(h && w && send_idx && peer_h && peer_w && peer_flag && dst_off && src_begin && count && ticket);
+    HaloPutArgs a;
+    a.h = h; a.w = w; a.send_idx = send_idx; a.npeers = npeers; a.flag_value = flag_value;
+    a.ticket = (unsigned int *)ticket;
+    int64_t total = 0;
+    for (int p = 0; p < npeers; ++p) {
+        NXB_ARG(src_begin[p] == total && count[p] >= 0);
+        a.peer[p].h = (float *)peer_h[p]; a.peer[p].w = (float *)peer_w[p]; a.peer[p].flag = (uint32_t *)peer_flag[p];
+        a.peer[p].dst_off = dst_off[p]; a.peer[p].src_begin = src_begin[p]; a.peer[p].count = count[p];
+        total += count[p];
+    }
+    for (int p = npeers; p < HALO_MAX_PEERS; ++p) { a.peer[p] = a.peer[0]; a.peer[p].src_begin = total; a.peer[p].count = 0; }
+    a.total = total;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 2 * nxb_sm_count()) blocks = 2 * nxb_sm_count();
+    halo_put_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
+__global__ void halo_wait_kernel(const uint32_t *flags, const int32_t *src_ranks, int npeers, uint32_t target)
+{
+    if ((int)threadIdx.x < npeers) {
+        const volatile uint32_t *f = flags + src_ranks[threadIdx.x];
+        // flags only grow; wrap-safe comparison
+        while ((int32_t)(*f - target) < 0) { __nanosleep(20); }
+    }
+    __threadfence_system();
+}
+
+// flags: this rank's flag array (one uint32 per source rank); src_ranks: device int32[npeers]
+NXB_API int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, void *stream)
+{
+    NXB_ARG(npeers >= 0 && npeers <= 32);
+    if (npeers == 0) return NXB_OK;
+    NXB_ARG(flags && src_ranks);
+    halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const uint32_t *)flags, src_ranks, npeers, target);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}

@@ -27,9 +27,11 @@ def find_percent_val(minval, maxval, percent):
 class Collective:
     """The handful of scalar exchanges the sharded assembly needs.  world=1: identity."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, distributed=False):
+        """distributed=False (default): single-domain, never touches torch.distributed even if a
+        process group exists (a rank may run a whole-planet reference next to the sharded run)."""
         import torch.distributed as dist
-        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.dist = dist if (distributed and dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0

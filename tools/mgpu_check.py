@@ -1,0 +1,70 @@
+"""torchrun --nproc-per-node N tools/mgpu_check.py : sharded == single-GPU (bit-identical) + timings."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.distributed as dist
+from nixis_b200 import runtime as rt
+from nixis_b200.multigpu import ShardedTerrain
+from nixis_b200.pipeline import TerrainPipeline
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+def gather_own(t, terr):
+    sizes = [e - b for b, e in terr.ranges]
+    out = [torch.empty(s, dtype=t.dtype, device=t.device) for s in sizes]
+    # all_gather with unequal sizes: pad
+    m = max(sizes)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device); pad[: t.numel()] = t
+    bufs = [torch.empty(m, dtype=t.dtype, device=t.device) for _ in sizes]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+for transport in ("nvlink", "p2p"):
+    for k, sweeps in ((64, 25), (200, 10)):
+        terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
+        h, ocean, lvl = terr.heights()
+        terr.erosion.load(h)
+        terr.erosion.run(sweeps)
+        terr.erosion.finish()
+        torch.cuda.synchronize()
+        H = gather_own(terr.erosion.heights.contiguous(), terr)
+        W = gather_own(terr.erosion.water.contiguous(), terr)
+        S = gather_own(terr.erosion.sediment.contiguous(), terr)
+        if rank == 0:
+            pipe = TerrainPipeline(k, seed=12345, n_octaves=8)
+            pipe.build_mesh()
+            h1, _, lvl1 = pipe.heights()
+            st = pipe.erosion_state(h1)
+            st.run(sweeps)
+            torch.cuda.synchronize()
+            same = (torch.equal(H, st.heights), torch.equal(W, st.water), torch.equal(S, st.sediment))
+            print(f"[{transport}] k={k} world={world} sweeps={sweeps}: bit-identical h/w/s = {same}  level {lvl} vs {lvl1}  "
+                  f"halo {terr.plan.n_halo} irregular tiles {terr.erosion.tile_plan.n_irregular}/{terr.erosion.tile_plan.n_tiles}", flush=True)
+            assert all(same), "sharded result differs from single GPU"
+        dist.barrier()
+        del terr
+        torch.cuda.empty_cache()
+
+# timings at scale
+k = int(os.environ.get("MGPU_K", "2500"))
+for transport in ("nvlink", "p2p"):
+    terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
+    h, _, _ = terr.heights()
+    ero = terr.erosion
+    for n in (50, 300):
+        ero.load(h)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ero.run(n); ero.finish(); e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"[{transport}] k={k} world={world}: {n} sweeps {ms.item():.2f} ms -> {ms.item()/n*1e3:.1f} us/sweep, "
+                  f"{terr.V*n/ms.item()/1e3:.0f} Mvert-iter/s; n_own {terr.n_own} halo {terr.plan.n_halo} "
+                  f"irregular {ero.tile_plan.n_irregular}/{ero.tile_plan.n_tiles}", flush=True)
+    t0 = time.perf_counter(); hh, _, _ = terr.heights(); torch.cuda.synchronize(); dist.barrier()
+    if rank == 0: print(f"[{transport}] fbm+assembly {1e3*(time.perf_counter()-t0):.2f} ms", flush=True)
+    del terr, ero
+    torch.cuda.empty_cache()
+dist.destroy_process_group()
