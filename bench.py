@@ -180,7 +180,7 @@ def workload_config(args):
     return {"workload": f"icosphere d={args.division} ({10 * args.division ** 2 + 2} verts), {args.octaves}-octave "
                         f"OpenSimplex fBm + height assembly + {args.iters} erosion_iteration3 sweeps, seed {args.seed}, R=1",
             "division": args.division, "octaves": args.octaves, "erosion_iters": args.iters,
-            "l2": "inputs larger than L2 (state 3x250 MB + adjacency 1.5 GB + xyz 1 GB per sweep)",
+            "l2": "inputs larger than L2: every sweep streams 3.75 GB (h/w/s in+out 1.5 GB, 16-bit adjacency 0.75 GB, edge lengths 1.5 GB) vs 126 MB of L2; no flush needed",
             "parallelism": f"vertex-range shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
 
 
@@ -262,11 +262,11 @@ def run_ours(args):
     ero_launch_ms = ero_ms / iters
     ero_gbs = BYTES_PER_VERT_ITER * V / (ero_launch_ms * 1e-3) / 1e9
     fbm_tflops = FLOP_PER_VERT_OCT * V * n_oct / (fbm_ms * 1e-3) / 1e12
-    roofline = {"kernel": "erode3_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "erode3_plan_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ero_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_VERT_ITER * V, "avg_launch_ms": ero_launch_ms}
     fbm_obj = {"value": V * n_oct / (fbm_ms * 1e-3) / 1e6, "unit": "Mvert*octaves/s", "ms": fbm_ms,
-               "roofline": {"kernel": "fbm_kernel<3>", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
+               "roofline": {"kernel": "fbm3_fast_kernel", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
                             "unit": "TFLOP/s", "frac": fbm_tflops / fp32_peak,
                             "peak_source": "measured here: nxb_ffma_peak FFMA microbenchmark",
                             "algorithmic_flop_per_vert_octave": FLOP_PER_VERT_OCT}}
