@@ -77,6 +77,28 @@ def test_noise2_vs_reference_golden(nx, golden, seed):
     assert (err[:4000] <= 2e-5).all() and (err <= 2.5e-4 + 1.0e-6 * mag).all(), err.max()
 
 
+@pytest.mark.parametrize("seed", [0, 12345])
+def test_noise4_vs_reference_golden(nx, golden, seed):
+    g = golden("noise")
+    perm, _ = nx.osi.init(seed)
+    p, ref = g[f"p4_{seed}"], g[f"v4_{seed}"]
+    got = nx.osi.noisearr4d(p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy(), p[:, 3].copy(), perm)
+    mag = np.abs(p).max(axis=1)
+    err = np.abs(got - ref)
+    assert err[:6000].max() <= 3e-5 and np.quantile(err[:6000], 0.999) < 1e-5, err[:6000].max()
+    assert (err <= 5e-4 + 2.0e-6 * mag).all(), err.max()          # far points / exact lattice ties
+
+
+def test_sample_octaves4_vs_oracle(nx, oracle):
+    """4-D fBm driver (builder-defined: w = 0.5 * frequency) against the float64 oracle, 12 octaves."""
+    pts, _ = icosphere.icosa_sphere(24)
+    perm, _ = nx.osi.init(42)
+    got = nx.terrain.sample_octaves4(pts, None, perm, 12, 1.5, 0.4, 2.5, 0.5, 1.0)
+    ref = oracle.sample_octaves4(pts, None, perm, 12, 1.5, 0.4, 2.5, 0.5, 1.0)
+    assert relerr(got, ref) <= 4e-5, relerr(got, ref)
+    assert abs(nx.osi.noise4d(.1, .2, .3, .4, perm) - oracle.noise4d(.1, .2, .3, .4, perm)) < 5e-6
+
+
 def test_noise_scalar_api(nx):
     perm, pgi = nx.osi.init(12345)
     assert abs(nx.osi.noise3d(.1, .2, .3, perm, pgi) - 0.4740432999870549) < 5e-6
