@@ -148,6 +148,24 @@ int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const flo
                              const float *h_in, const float *w_in, const float *s_in,
                              float *h_out, float *w_out, float *s_out,
                              int64_t n_own, float rain, void *stream);
+/* The same sweep fused with the multi-GPU halo exchange in ONE kernel: boundary results are stored
+ * straight into the peers' halo slots over NVLink as they are computed, the kernel waits for the
+ * peers' flags only before the first tile that reads halo data, and the last CTA raises this rank's
+ * flag (flag_value) in every peer.  send_ptr/send_entries: device CSR per tile of {int32 dst,
+ * uint16 vertex-in-tile, uint16 peer slot}; peer_h/peer_w/peer_flag: host arrays of NVLink-mapped
+ * pointers (peers' OUTPUT buffers of this sweep, their flag slot for this rank); flags: this rank's
+ * uint32 flag array; wait_rank: host int32[n_wait]; halo_begin: first halo slot; ticket: device
+ * uint32 (zero). */
+int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+                                  const float *h_in, const float *w_in, const float *s_in,
+                                  float *h_out, float *w_out, float *s_out,
+                                  int64_t n_own, float rain,
+                                  const int32_t *send_ptr, const void *send_entries, int n_send_peers,
+                                  void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+                                  const void *flags, const int32_t *wait_rank, int n_wait,
+                                  uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
+                                  void *ticket, const int32_t *tile_order /* nullable: processing order */,
+                                  void *stream);
 /* erosion.py:76-99 erosion_iteration1 */
 int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
                         int64_t v_begin, int64_t v_end, void *stream);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "nxb_erode_plan_bytes": (_i64, [_i64]),
     "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
+    "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
+                                           _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "nxb_halo_put_f32": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
     "nxb_halo_wait": (_i, [_p, _p, _i, C.c_uint32, _p]),

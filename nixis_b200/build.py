@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "libnixis_b200.so")
 SOURCES = ["nxb_api.cu", "nxb_noise.cu", "nxb_mesh.cu", "nxb_adjacency.cu", "nxb_assembly.cu",
            "nxb_erosion.cu", "nxb_halo.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "-DNXB_HAVE_NOISE4"]
+              "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "-DNXB_HAVE_NOISE4"] + (["-DNXB_ERO_DEBUG_WAIT"] if os.environ.get("NXB_ERO_DEBUG_WAIT") else [])
 
 
 def _nvcc():

@@ -26,6 +26,7 @@
 //     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
 #include "nxb_common.cuh"
 #include "nxb_erosion_plan.cuh"
+#include <string.h>
 
 #define ERO_STAGES 4
 #define ERO_CONSUMER_WARPS (ERO_TILE / 32)
@@ -38,7 +39,38 @@ struct __align__(128) EroStage {
     float dist[ERO_TILE * 6];
     uint16_t adj[ERO_TILE * 6];
     int32_t irregular;
-    int32_t pad[31];
+    int32_t tile;
+    int32_t pad[30];
+};
+
+#define ERO_MAX_PEERS 8
+
+// One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` of peer slot
+// `peer`'s output buffers.  Entries are grouped by tile (CSR: send_ptr[tile] .. send_ptr[tile+1]).
+struct EroSendEntry { int32_t dst; uint16_t c; uint16_t peer; };
+
+// Fused halo exchange (multi-GPU shards; all pointers null / counts zero on a single GPU):
+//   * consumers store the freshly computed h / w of boundary vertices straight into the peers'
+//     halo slots (NVLink-mapped peer memory) right after computing them;
+//   * the producer warp spins on this rank's flag words only before the first tile that needs halo
+//     data (a segment in the halo area, or an irregular tile);
+//   * the last CTA to finish raises this rank's flag in every peer (after system-scope fences).
+struct EroComm {
+    const int32_t *send_ptr;            // [n_tiles + 1], null = no sends
+    const EroSendEntry *send_entries;
+    float *peer_h[ERO_MAX_PEERS], *peer_w[ERO_MAX_PEERS];   // peers' OUTPUT buffers of this sweep
+    uint32_t *peer_flag[ERO_MAX_PEERS]; // peers' flag slot for this rank
+    int n_send_peers;
+    const uint32_t *flags;              // this rank's flag array (written by the peers)
+    int32_t wait_rank[ERO_MAX_PEERS];
+    int n_wait;
+    uint32_t wait_target, flag_value;
+    int64_t halo_begin;                 // first halo slot (n_own_pad)
+    unsigned int *ticket;
+    // processing order of the tiles (null = index order).  The sharded driver puts the tiles that
+    // read halo slots LAST, so by the time a CTA reaches them the peers' flags are already up and
+    // the wait hides behind interior work.
+    const int32_t *tile_order;
 };
 
 struct EroPlanArgs {
@@ -49,6 +81,7 @@ struct EroPlanArgs {
     float *h_out, *w_out, *s_out;
     int64_t n_own;
     float rain;
+    EroComm comm;
 };
 
 // erosion.py:210-267 for one vertex, neighbour values already fetched.
@@ -80,6 +113,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EroStage *stage = reinterpret_cast<EroStage *>(smem_raw);
     __shared__ __align__(8) uint64_t full[ERO_STAGES], empty[ERO_STAGES];
+    __shared__ float send_h[ERO_TILE], send_w[ERO_TILE];
+    __shared__ bool s_last;
+    bool cta_sent = false;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (a.n_own + ERO_TILE - 1) / ERO_TILE;
@@ -92,18 +128,36 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     }
     __syncthreads();
 
+#ifdef NXB_ERO_DEBUG_WAIT
+    unsigned long long dbg_t0 = 0; long long dbg_c0 = 0;
+    if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+        dbg_c0 = clock64();
+        a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 0] = (unsigned)dbg_t0;
+    }
+#endif
     if (warp == 0) {
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
         const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
         int32_t word = 0;                       // this lane's word of the 16-word descriptor
-        if (my_tiles > 0 && lane < 16) word = __ldg(dw + (int64_t)blockIdx.x * 16 + lane);
+        bool halo_ready = a.comm.n_wait == 0;
+        const int32_t *order = a.comm.tile_order;
+        auto tile_of = [&](int64_t i) -> int64_t {       // i-th tile of this CTA
+            const int64_t slot = blockIdx.x + i * gridDim.x;
+            return order ? (int64_t)__ldg(order + slot) : slot;
+        };
+        int64_t tile = my_tiles > 0 ? tile_of(0) : 0;
+        int64_t tile_next = my_tiles > 1 ? tile_of(1) : 0;
+        if (my_tiles > 0 && lane < 16) word = __ldg(dw + tile * 16 + lane);
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int s = (int)(it % ERO_STAGES);
-            const int64_t tile = blockIdx.x + it * gridDim.x;
             const int64_t v0 = tile * ERO_TILE;
+            const int32_t tile_id = (int32_t)tile;
             // descriptor words: 0..5 seg_start | 6..8 seg_len pairs | 9..11 seg_off pairs | 12 nseg | 13 irregular | 14 halo_used
             const int32_t cur = word;
-            if (it + 1 < my_tiles && lane < 16) word = __ldg(dw + (tile + gridDim.x) * 16 + lane);
+            if (it + 1 < my_tiles && lane < 16) word = __ldg(dw + tile_next * 16 + lane);
+            tile = tile_next;
+            if (it + 2 < my_tiles) tile_next = tile_of(it + 2);
             const int nseg = __shfl_sync(0xffffffffu, cur, 12);
             const int irregular = __shfl_sync(0xffffffffu, cur, 13);
             const int halo_used = __shfl_sync(0xffffffffu, cur, 14);
@@ -114,10 +168,44 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, 9 + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
+            if (!halo_ready) {
+                // does this tile read halo slots?  (a segment in the halo area, or global gathers)
+                const bool mine = (q >= 0 && q < nseg && (int64_t)seg_start >= a.comm.halo_begin) || irregular;
+                if (__any_sync(0xffffffffu, mine)) {
+                    if (lane < a.comm.n_wait) {
+                        const volatile uint32_t *f = a.comm.flags + a.comm.wait_rank[lane];
+                        // gentle polling: hundreds of CTAs hammering one L2 line delay the very
+                        // NVLink write they are waiting for
+                        unsigned ns = 64;
+#ifdef NXB_ERO_DEBUG_WAIT
+                        unsigned long long t0, t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                        bool spun = false;
+#endif
+                        while ((int32_t)(*f - a.comm.wait_target) < 0) {
+                            __nanosleep(ns); if (ns < 1024) ns *= 2;
+#ifdef NXB_ERO_DEBUG_WAIT
+                            spun = true;
+#endif
+                        }
+#ifdef NXB_ERO_DEBUG_WAIT
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (spun) { atomicAdd(a.comm.ticket + 1, 1u); atomicMax(a.comm.ticket + 2, (unsigned)(t1 - t0)); }
+                        atomicMax(a.comm.ticket + 3, (unsigned)it);
+                        if (blockIdx.x == 0 && lane == 0) a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 1] = (unsigned)t1;
+#endif
+                    }
+                    __threadfence_system();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __syncwarp();
+                    halo_ready = true;
+                }
+            }
             nxb_mbar_wait(&empty[s], (uint32_t)(((it / ERO_STAGES) & 1) ^ 1));
             EroStage &st = stage[s];
             if (lane == 0) {
                 st.irregular = irregular;
+                st.tile = tile_id;
                 const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
                 nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
                 nxb_bulk_g2s(st.h, a.h_in + v0, ERO_TILE * 4, &full[s]);
@@ -136,9 +224,10 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const int c = tid - 32;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int s = (int)(it % ERO_STAGES);
-            const int64_t v = (blockIdx.x + it * gridDim.x) * (int64_t)ERO_TILE + c;
             nxb_mbar_wait(&full[s], (uint32_t)((it / ERO_STAGES) & 1));
             const EroStage &st = stage[s];
+            const int64_t tile = st.tile;
+            const int64_t v = tile * (int64_t)ERO_TILE + c;
             float hn[6], wn[6], d[6];
             {
                 const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
@@ -169,6 +258,48 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             float hh, ww, ss;
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
             if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
+            if (a.comm.send_ptr) {
+                const int32_t e0 = __ldg(a.comm.send_ptr + tile), e1 = __ldg(a.comm.send_ptr + tile + 1);
+                if (e1 > e0) {                  // uniform over the 8 consumer warps
+                    send_h[c] = hh; send_w[c] = ww;
+                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
+                    for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
+                        const EroSendEntry en = a.comm.send_entries[e];
+                        a.comm.peer_h[en.peer][en.dst] = send_h[en.c];
+                        a.comm.peer_w[en.peer][en.dst] = send_w[en.c];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
+                    cta_sent = true;
+                }
+            }
+        }
+    }
+#ifdef NXB_ERO_DEBUG_WAIT
+    if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {       // SM clock (MHz) seen by CTA 0 over its lifetime
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        long long c1 = clock64();
+        a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 3] = (unsigned)((c1 - dbg_c0) * 1000 / (long long)(t1 - dbg_t0 + 1));
+    }
+#endif
+    if (a.comm.n_send_peers > 0) {
+        // every peer store of this CTA is visible system-wide before the CTA checks in; the last
+        // CTA of the grid then raises this rank's flag in every peer
+        if (cta_sent) __threadfence_system();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            if (tid < a.comm.n_send_peers) {
+                __threadfence_system();
+                volatile uint32_t *f = a.comm.peer_flag[tid];
+                *f = a.comm.flag_value;
+                __threadfence_system();
+            }
+            if (tid == 0) *a.comm.ticket = 0;
+#ifdef NXB_ERO_DEBUG_WAIT
+            if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                            a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
+#endif
         }
     }
 }
@@ -276,10 +407,10 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
 
 static bool g_ero_attr_set[64] = {false};
 
-NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
-                                     const float *h_in, const float *w_in, const float *s_in,
-                                     float *h_out, float *w_out, float *s_out,
-                                     int64_t n_own, float rain, void *stream)
+static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const float *dist,
+                              const float *h_in, const float *w_in, const float *s_in,
+                              float *h_out, float *w_out, float *s_out,
+                              int64_t n_own, float rain, const EroComm &comm, void *stream)
 {
     NXB_ARG(n_own >= 0);
     if (n_own == 0) return NXB_OK;
@@ -294,6 +425,7 @@ NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, c
     a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
     a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
     a.n_own = n_own; a.rain = rain;
+    a.comm = comm;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
     const size_t smem = sizeof(EroStage) * ERO_STAGES;
@@ -305,6 +437,53 @@ NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, c
     erode3_plan_kernel<<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
+}
+
+NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+                                     const float *h_in, const float *w_in, const float *s_in,
+                                     float *h_out, float *w_out, float *s_out,
+                                     int64_t n_own, float rain, void *stream)
+{
+    EroComm comm;
+    memset(&comm, 0, sizeof comm);
+    return erode3_plan_launch(plan_mem, adj, dist, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
+}
+
+// Sweep + halo exchange in ONE kernel (see EroComm).  send_ptr / send_entries: device CSR of
+// {int32 dst, uint16 vertex-in-tile, uint16 peer slot}; peer_h / peer_w / peer_flag: host arrays of
+// n_send_peers NVLink-mapped pointers (the peers' OUTPUT buffers of this sweep and their flag slot
+// for this rank); flags: this rank's flag array; wait_rank: host int32[n_wait] source ranks whose
+// flag must reach wait_target before halo slots are read; flag_value: raised in the peers when the
+// whole grid has finished; halo_begin: first halo slot; ticket: device uint32, zero.
+NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+                                          const float *h_in, const float *w_in, const float *s_in,
+                                          float *h_out, float *w_out, float *s_out,
+                                          int64_t n_own, float rain,
+                                          const int32_t *send_ptr, const void *send_entries, int n_send_peers,
+                                          void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+                                          const void *flags, const int32_t *wait_rank, int n_wait,
+                                          uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
+                                          void *ticket, const int32_t *tile_order, void *stream)
+{
+    NXB_ARG(n_send_peers >= 0 && n_send_peers <= ERO_MAX_PEERS && n_wait >= 0 && n_wait <= ERO_MAX_PEERS);
+    NXB_ARG(n_send_peers == 0 || (send_ptr && send_entries && peer_h && peer_w && peer_flag && ticket));
+    NXB_ARG(n_wait == 0 || (flags && wait_rank));
+    EroComm comm;
+    memset(&comm, 0, sizeof comm);
+    if (n_send_peers > 0) {
+        comm.send_ptr = send_ptr; comm.send_entries = (const EroSendEntry *)send_entries;
+        for (int p = 0; p < n_send_peers; ++p) {
+            comm.peer_h[p] = (float *)peer_h[p]; comm.peer_w[p] = (float *)peer_w[p]; comm.peer_flag[p] = (uint32_t *)peer_flag[p];
+        }
+        comm.n_send_peers = n_send_peers;
+        comm.ticket = (unsigned int *)ticket;
+    }
+    comm.flags = (const uint32_t *)flags;
+    for (int p = 0; p < n_wait; ++p) comm.wait_rank[p] = wait_rank[p];
+    comm.n_wait = n_wait;
+    comm.wait_target = wait_target; comm.flag_value = flag_value; comm.halo_begin = halo_begin;
+    comm.tile_order = tile_order;
+    return erode3_plan_launch(plan_mem, adj, dist, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

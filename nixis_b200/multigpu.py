@@ -2,11 +2,13 @@
 
 fBm / height assembly: every rank works on its own contiguous vertex range; the only exchange is a
 handful of scalars (global min/max, power_rescale statistics) through all_reduce / all_gather.
-Erosion: one halo exchange of boundary h / w per sweep (partition.py).  Two transports:
-  * "nvlink": state buffers live in torch symmetric memory, the peers' addresses are mapped into
-    this process, and hand-written kernels put the boundary values straight into the peers' halo
-    slots and raise a flag (csrc/nxb_halo.cu) -- three kernel launches per sweep (wait, sweep, put),
-    no NCCL call, no host synchronisation;
+Erosion: one halo exchange of boundary h / w per sweep (partition.py).  Three transports:
+  * "fused" (default): state buffers live in torch symmetric memory, the peers' addresses are mapped
+    into this process, and the sweep kernel itself stores boundary results into the peers' halo slots
+    over NVLink as it computes them and raises this rank's flag from its last CTA
+    (csrc/nxb_erosion.cu, EroComm); a one-warp kernel waits for the peers' flags before the next
+    sweep -- two launches per sweep, no NCCL call, no host synchronisation;
+  * "nvlink": same memory, but separate wait / sweep / put kernels (csrc/nxb_halo.cu);
   * "p2p": torch.distributed batch_isend_irecv (NCCL on GPUs, gloo in the CPU tests) -- the baseline
     and fallback.
 """
@@ -37,7 +39,7 @@ def _i64_array(values):
 class ShardedErosion:
     """Erosion state of one rank: padded own range + halo slots, ping-pong (h, w, s)."""
 
-    def __init__(self, plan: RankPlan, dist_f32, transport="nvlink", group=None):
+    def __init__(self, plan: RankPlan, dist_f32, transport="fused", group=None):
         self.plan, self.group = plan, group
         self.rank, self.world = plan.rank, plan.world
         dev = plan.local_adj.device
@@ -53,7 +55,7 @@ class ShardedErosion:
         self.sweeps = 0                     # total sweeps since creation (flag values)
         self.flag_base = 0
         n_state = 4 * self.cap              # hA wA hB wB
-        if self.transport == "nvlink":
+        if self.transport in ("nvlink", "fused"):
             import torch.distributed._symmetric_memory as symm
             self._symm = symm
             try:
@@ -72,7 +74,7 @@ class ShardedErosion:
         self.hw = [(self._buf[0:c], self._buf[c:2 * c]), (self._buf[2 * c:3 * c], self._buf[3 * c:4 * c])]
         self.sed = [torch.zeros(c, dtype=torch.float32, device=dev), torch.zeros(c, dtype=torch.float32, device=dev)]
         self.flags = self._buf[4 * c:4 * c + 64].view(torch.int32)      # one uint32 per source rank
-        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(4 + 128, dtype=torch.int32, device=dev)
         self.cur = 0
         self._pending = False               # a publish has been issued whose incoming flags were not awaited yet
         # concatenated send list, peer after peer
@@ -87,8 +89,43 @@ class ShardedErosion:
         self._src_begin = _i64_array(np.concatenate([[0], np.cumsum(counts)[:-1]]) if counts else [])
         self._dst_off = _i64_array([plan.peer_n_own_pad[p] + plan.send_dst_offset[p] for p in self.send_peers])
         self.recv_ranks = torch.tensor(self.recv_peers if self.recv_peers else [0], dtype=torch.int32, device=dev)
+        if self.transport == "fused":
+            self._build_send_table()
         if self.world > 1:
             dist.barrier(group=group)
+
+    def _build_send_table(self):
+        """Per-tile CSR of {dst, vertex-in-tile, peer slot} for the fused sweep (EroSendEntry)."""
+        plan, dev = self.plan, self.device
+        n_tiles = (plan.n_own + TILE - 1) // TILE
+        vs, dsts, slots = [], [], []
+        for slot, p in enumerate(self.send_peers):
+            idx = plan.send_idx[p].to(torch.int64)
+            base = plan.peer_n_own_pad[p] + plan.send_dst_offset[p]
+            vs.append(idx)
+            dsts.append(base + torch.arange(idx.numel(), dtype=torch.int64, device=dev))
+            slots.append(torch.full_like(idx, slot))
+        if vs:
+            v, dst, slot = torch.cat(vs), torch.cat(dsts), torch.cat(slots)
+            order = torch.argsort(v // TILE, stable=True)
+            v, dst, slot = v[order], dst[order], slot[order]
+            counts = torch.bincount(v // TILE, minlength=n_tiles)
+            packed = (dst & 0xFFFFFFFF) | ((v % TILE) << 32) | (slot << 48)       # little-endian {i32, u16, u16}
+            self.send_entries = packed.contiguous()
+        else:
+            counts = torch.zeros(n_tiles, dtype=torch.int64, device=dev)
+            self.send_entries = torch.zeros(1, dtype=torch.int64, device=dev)
+        ptr = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(counts, 0)
+        self.send_ptr = ptr.to(torch.int32).contiguous()
+        self._wait_rank = (C.c_int32 * max(1, len(self.recv_peers)))(*self.recv_peers)
+        # processing order: tiles that read halo slots (a halo segment, or irregular) go last
+        desc = self.tile_plan.mem[: n_tiles * 64].view(torch.int32).view(n_tiles, 16)
+        seg_start, nseg, irregular = desc[:, 0:6].to(torch.int64), desc[:, 12:13], desc[:, 13]
+        live = torch.arange(6, device=dev).unsqueeze(0) < nseg
+        needs_halo = ((seg_start >= plan.n_own_pad) & live).any(dim=1) | (irregular != 0)
+        self.tile_order = torch.argsort(needs_halo.to(torch.int8), stable=True).to(torch.int32).contiguous()
+        self.n_halo_tiles = int(needs_halo.sum().item())
 
     # ------------------------------------------------------------------------------------
     def load(self, heights_own):
@@ -112,15 +149,10 @@ class ShardedErosion:
             return
         self._pending = True
         h, w = self.hw[which]
-        if self.transport == "nvlink":
+        if self.transport in ("nvlink", "fused"):
             if not self.send_peers:
                 return
-            c = self.cap
-            off_h = (0 if which == 0 else 2 * c) * 4
-            off_w = (c if which == 0 else 3 * c) * 4
-            ph = _ptr_array([self._peer_base[p] + off_h for p in self.send_peers])
-            pw = _ptr_array([self._peer_base[p] + off_w for p in self.send_peers])
-            pf = _ptr_array([self._peer_base[p] + 4 * c * 4 + 4 * self.rank for p in self.send_peers])
+            ph, pw, pf = self._peer_ptrs(which)
             _lib.call("nxb_halo_put_f32", rt._ptr(h), rt._ptr(w), rt._ptr(self.send_idx), len(self.send_peers),
                       ph, pw, pf, self._dst_off, self._src_begin, self._count,
                       C.c_uint32(self.sweeps + 1), rt._ptr(self.ticket), rt._stream())
@@ -129,14 +161,47 @@ class ShardedErosion:
 
     def _await(self):
         self._pending = False
-        if self.world > 1 and self.transport == "nvlink" and self.recv_peers:
+        if self.world > 1 and self.transport in ("nvlink", "fused") and self.recv_peers:
             _lib.call("nxb_halo_wait", rt._ptr(self.flags), rt._ptr(self.recv_ranks), len(self.recv_peers),
                       C.c_uint32(self.sweeps + 1), rt._stream())
 
+    def _peer_ptrs(self, which):
+        c = self.cap
+        off_h = (0 if which == 0 else 2 * c) * 4
+        off_w = (c if which == 0 else 3 * c) * 4
+        return (_ptr_array([self._peer_base[p] + off_h for p in self.send_peers]),
+                _ptr_array([self._peer_base[p] + off_w for p in self.send_peers]),
+                _ptr_array([self._peer_base[p] + 4 * c * 4 + 4 * self.rank for p in self.send_peers]))
+
     def step(self, rain=RAIN_AMOUNT):
-        self._await()
         src = self.hw[self.cur] + (self.sed[self.cur],)
         dst = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
+        if self.transport == "fused" and self.world > 1:
+            # one kernel: wait (only where halo data is read) + sweep + put + flag
+            ph, pw, pf = self._peer_ptrs(1 - self.cur)
+            tp = self.tile_plan
+            # The flag wait stays a tiny stream-ordered kernel: waiting INSIDE the sweep (n_wait > 0,
+            # NXB_FUSED_INKERNEL_WAIT=1) works and is bit-identical, but measured bistable on 2 GPUs --
+            # the ranks either stay in lockstep (333 us/sweep) or fall into a wait/compute alternation
+            # (635 us/sweep); see profiles/r01_fused_wait_timeline.txt.
+            n_wait, wait_target, order = 0, 0, None
+            if os.environ.get("NXB_FUSED_INKERNEL_WAIT"):
+                n_wait, wait_target = len(self.recv_peers), self.sweeps + 1
+                order = rt._ptr(self.tile_order) if os.environ.get("NXB_FUSED_TILE_ORDER") else None
+            else:
+                self._await()
+            _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
+                      rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
+                      tp.n_own, C.c_float(rain),
+                      rt._ptr(self.send_ptr), rt._ptr(self.send_entries), len(self.send_peers), ph, pw, pf,
+                      rt._ptr(self.flags), self._wait_rank, n_wait,
+                      C.c_uint32(wait_target), C.c_uint32(self.sweeps + 2), self.plan.n_own_pad,
+                      rt._ptr(self.ticket), order, rt._stream())
+            self._pending = True
+            self.cur = 1 - self.cur
+            self.sweeps += 1
+            return
+        self._await()
         rt.erode3_step(self.tile_plan, self.dist, src, dst, rain)
         self.cur = 1 - self.cur
         self.sweeps += 1
@@ -166,7 +231,7 @@ class ShardedErosion:
 class ShardedTerrain:
     """One rank's share of the whole hot path."""
 
-    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, transport="nvlink", group=None):
+    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, transport="fused", group=None):
         rt.require_cuda()
         self.k, self.radius, self.group = int(k), float(radius), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -213,7 +278,7 @@ def run_multi_gpu_bench(args, rank, world, local):
     import bench as B
 
     k, n_oct, iters = args.division, args.octaves, args.iters
-    transport = os.environ.get("NXB_HALO", "nvlink")
+    transport = os.environ.get("NXB_HALO", "fused")
     terr = ShardedTerrain(k, seed=args.seed, n_octaves=n_oct, radius=1.0, transport=transport)
     V, n_own = terr.V, terr.n_own
     ero = terr.erosion
