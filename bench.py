@@ -60,17 +60,24 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -91,11 +98,17 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+        lo = (self.t_begin or 0) - 0.05
+        hi = (self.t_end or 1e18) + 0.05
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if not (lo <= ts <= hi):
+                    continue            # sample outside the timed region (the sampler starts before warm-up)
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
@@ -230,20 +243,22 @@ def run_ours(args):
         if timed is not None:
             timed.append(e)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count
     timed = []
     t_start, t_end = ev(), ev()
     torch.cuda.synchronize()
+    sampler.mark_begin()
     t_start.record()
     for _ in range(args.steps):
         step(timed)
     t_end.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = _lib.launch_count - launches0
     total_ms = t_start.elapsed_time(t_end)

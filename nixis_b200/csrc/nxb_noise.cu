@@ -184,12 +184,22 @@ fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ x
                  const __grid_constant__ FbmFastParams prm, const float *__restrict__ init,
                  float *__restrict__ out, float *__restrict__ minmax)
 {
-    extern __shared__ __align__(128) char nxf_sm[];
+    extern __shared__ __align__(128) char nxf_raw[];
+    // tables start at a 32 KB-aligned shared address: a lookup address is then (hash & MASK) | lane4
+    const uint32_t raw_sa = nxb_smem_u32(nxf_raw);
+    const uint32_t base_sa = (raw_sa + 32767u) & ~32767u;
+    char *nxf_sm = nxf_raw + (base_sa - raw_sa);
     nxf_build_tables(tab->perm8, tab->grad8, nxf_sm, threadIdx.x, blockDim.x);
     __syncthreads();
-    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
+    const uint32_t lane4 = base_sa | ((threadIdx.x & 31u) * 4u);
     float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    // The trip count is WARP-UNIFORM (the selection uses full-mask warp votes): a lane past the end
+    // of the array evaluates the last vertex again and simply does not store.
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t vv = base + (threadIdx.x & 31u);
+        const bool live = vv < n;
+        const int64_t v = live ? vv : n - 1;
         const float4 p = __ldg(xyz + v);
         float acc = init ? init[v] : 0.0f;
 #pragma unroll 1
@@ -198,7 +208,7 @@ fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ x
             acc = fmaf(nxf_noise3_x103(p.x * f, p.y * f, p.z * f, nxf_sm, lane4), prm.amp[o], acc);
         }
         acc += prm.base;
-        out[v] = acc;
+        if (live) out[v] = acc;
         lo = fminf(lo, acc);
         hi = fmaxf(hi, acc);
     }
@@ -224,11 +234,11 @@ static int fbm3_fast_launch(void *tables, const nxb_float4 *xyz_unit, int64_t n,
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !g_fbm_fast_attr[dev]) {
-        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NXF_SMEM_BYTES));
+        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NXF_SMEM_BYTES + 32768)));
         g_fbm_fast_attr[dev] = true;
     }
-    int grid = nxb_grid_resident(fbm3_fast_kernel, 1024, NXF_SMEM_BYTES, (n + 1023) / 1024);
-    fbm3_fast_kernel<<<grid, 1024, NXF_SMEM_BYTES, st>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, init, out, minmax);
+    int grid = nxb_grid_resident(fbm3_fast_kernel, 1024, NXF_SMEM_BYTES + 32768, (n + 1023) / 1024);
+    fbm3_fast_kernel<<<grid, 1024, NXF_SMEM_BYTES + 32768, st>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, init, out, minmax);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

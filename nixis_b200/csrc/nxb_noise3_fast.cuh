@@ -73,13 +73,34 @@ static const int8_t NXF_EXTRA_OFFSETS[19][3] = {
     {0, 0, 0}};
 
 struct NxfCtx {
-    const char *sm;         // shared-memory base of the tables
-    uint32_t lane4;         // lane * 4
+    const char *sm;         // shared-memory base of the tables (host build: plain pointer)
+    uint32_t lane4;         // lane * 4; on the device OR-ed with the 32 KB-aligned shared address of
+                            // the tables, so that (hash & MASK) | lane4 IS the load address
     uint32_t xb7, yb7, zb7; // (lattice base & 255) * 128, unmasked
     float dx0, dy0, dz0;
     float v;
 };
 
+#ifdef __CUDACC__
+// idx carries the absolute shared address (tables are 32 KB aligned): one LOP3 + one LDS per lookup,
+// table selected by the immediate offset.
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t nxf_ldu_t(uint32_t idx)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(idx), "n"(OFF));
+    return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ float nxf_ldf_t(uint32_t idx)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(idx), "n"(OFF));
+    return v;
+}
+#define nxf_ldu(c, off, idx) nxf_ldu_t<off>(idx)
+#define nxf_ldf(c, off, idx) nxf_ldf_t<off>(idx)
+#else
 NXF_DEV uint32_t nxf_ldu(const NxfCtx &c, uint32_t off, uint32_t idx)
 {
     return *reinterpret_cast<const uint32_t *>(c.sm + off + idx);
@@ -88,6 +109,7 @@ NXF_DEV float nxf_ldf(const NxfCtx &c, uint32_t off, uint32_t idx)
 {
     return *reinterpret_cast<const float *>(c.sm + off + idx);
 }
+#endif
 // one hash level: row ((h + add) & 255) of the P table, this lane's copy
 NXF_DEV uint32_t nxf_hash(const NxfCtx &c, uint32_t h_plus_add)
 {
@@ -133,36 +155,15 @@ NXF_DEV void nxf_pick2(float s0, float s1, float s2, int c0, int c1, int c2, int
     else if (as < bs && s2 > as) { as = s2; ap = c2; }
 }
 
-// x,y,z: lattice-space coordinates (vertex * octave frequency).  Returns noise3d * 103.
-NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_t lane4)
+// Candidate selection, literal form (one branch per lattice region, as the reference is written).
+// Kept as the specification the branch-free nxf_select below is checked against
+// (tools/host_noise_check.cpp compares them exactly, ties included).
+NXF_DEV void nxf_select_branchy(float fx, float fy, float fz, float fsum,
+                                float &T000, float &T100, float &T010, float &T001,
+                                float &T110, float &T101, float &T011, float &T111, int &e0, int &e1)
 {
-    const float MAGIC = 12582912.0f;   // 1.5 * 2^23: (x + MAGIC) - MAGIC rounds to nearest integer
-    const float so = (x + y + z) * (-1.0f / 6.0f);
-    const float xs = x + so, ys = y + so, zs = z + so;
-    const float tx = xs + MAGIC, ty = ys + MAGIC, tz = zs + MAGIC;
-    float bx = tx - MAGIC, by = ty - MAGIC, bz = tz - MAGIC;
-    // floor = round-to-nearest, minus 1 where that rounded up (opensimplex.py:18-21)
-    const bool ux = bx > xs, uy = by > ys, uz = bz > zs;
-    bx = ux ? bx - 1.0f : bx; by = uy ? by - 1.0f : by; bz = uz ? bz - 1.0f : bz;
-    NxfCtx c;
-    c.sm = sm; c.lane4 = lane4;
-    // low mantissa bits of (x + MAGIC) are the integer; only bits 0..7 survive the masks
-    c.xb7 = (nxf_as_uint(tx) - (ux ? 1u : 0u)) << 7;
-    c.yb7 = (nxf_as_uint(ty) - (uy ? 1u : 0u)) << 7;
-    c.zb7 = (nxf_as_uint(tz) - (uz ? 1u : 0u)) << 7;
-    const float fx = xs - bx, fy = ys - by, fz = zs - bz;
-    const float fsum = fx + fy + fz;
-    // position relative to the cell origin: f + fsum/3 (the un-skew of the in-cell coordinates;
-    // the reference's x - xb, opensimplex.py:283-297, is the same quantity)
-    c.dx0 = nxf_fma(fsum, 1.0f / 3.0f, fx);
-    c.dy0 = nxf_fma(fsum, 1.0f / 3.0f, fy);
-    c.dz0 = nxf_fma(fsum, 1.0f / 3.0f, fz);
-    c.v = 0.0f;
-
-    // ---- selection: live constants of the 8 cube corners + two extra codes ------------------
     const float LIVE = 2.0f, DEAD = -16.0f;
-    float T000, T100, T010, T001, T110, T101, T011, T111;
-    int e0, e1 = 18;
+    e1 = 18;
     if (fsum <= 1.0f) {                                    // tetrahedron at (0,0,0)
         int ap, bp; float as, bs;
         nxf_pick2(fx, fy, fz, 1, 2, 4, ap, as, bp, bs);
@@ -217,6 +218,116 @@ NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_
             e1 = 15 + ((c2 & 1) ? 0 : ((c2 & 2) ? 1 : 2));
         }
     }
+}
+
+#ifdef __CUDACC__
+#define NXF_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define NXF_ANY(p) (p)
+#endif
+
+// Candidate selection, branch-free form.  Same decisions as nxf_select_branchy:
+//   * the two tetrahedra share one routine: the (1,1,1) tetrahedron is the (0,0,0) one with the
+//     scores negated (exact in floating point), candidate i <-> axis i in both;
+//   * in every region the work is "keep the two best of three candidates" (nxf_pick2 semantics)
+//     followed by a two-way classification; candidates are tracked as axis numbers 0..2 and the
+//     extra codes / live corners are computed arithmetically from them;
+//   * the two blocks are skipped with a warp vote when no lane of the warp needs them, so a
+//     coherent warp pays for one block, a mixed warp for both, and no lane ever idles.
+NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
+                        float &T000, float &T100, float &T010, float &T001,
+                        float &T110, float &T101, float &T011, float &T111, int &e0, int &e1)
+{
+    const float LIVE = 2.0f, DEAD = -16.0f;
+    const bool r0 = fsum <= 1.0f, r1 = fsum >= 2.0f, tet = r0 || r1;
+    // outputs of the tetrahedron block
+    int te0 = 18, te1 = 18; bool opt0 = false, opt1 = false, opt2 = false;
+    if (NXF_ANY(tet)) {
+        const float s0 = r1 ? -fx : fx, s1 = r1 ? -fy : fy, s2 = r1 ? -fz : fz;
+        const float w = r1 ? fsum - 3.0f : 1.0f - fsum;
+        const bool ge = s0 >= s1;
+        const bool c1 = ge && s2 > s1;                  // newcomer replaces b
+        const bool c2 = !ge && s2 > s0;                 // newcomer replaces a
+        const float as = c2 ? s2 : s0, bs = c1 ? s2 : s1;
+        const int ia = c2 ? 2 : 0, ib = c1 ? 2 : 1;
+        const bool caseA = (w > as) || (w > bs);
+        const int cs = (bs > as) ? ib : ia;             // the single closest candidate (case A)
+        const int io = 3 - ia - ib;                     // the axis not among the two closest (case B)
+        // tet0: A -> extras 2cs, 2cs+1;            B -> cube corner omitting io + (1,1,1)-2e_io (12+io)
+        // tet1: A -> extras 10-2cs, 11-2cs;        B -> cube corner e_io         + 2e_io       (15+io)
+        const int a0 = r1 ? 10 - 2 * cs : 2 * cs;
+        const int b0 = (r1 ? 15 : 12) + io;
+        te0 = caseA ? a0 : b0;
+        te1 = caseA ? a0 + 1 : 18;
+        opt0 = !caseA && io == 0; opt1 = !caseA && io == 1; opt2 = !caseA && io == 2;
+    }
+    // outputs of the octahedron block
+    int oe0 = 18, oe1 = 18; bool near2 = false, far2 = false;
+    if (NXF_ANY(!tet)) {
+        const float p1 = fx + fy, p2 = fx + fz, p3 = fy + fz;
+        const bool f1 = p1 > 1.0f, f2 = p2 > 1.0f, f3 = p3 > 1.0f;
+        const float q1 = fabsf(p1 - 1.0f), q2 = fabsf(p2 - 1.0f), q3 = fabsf(p3 - 1.0f);
+        // reference: a <- p1, b <- p2; p3 replaces a if (as <= bs && as < sc), else b if (as > bs && bs < sc)
+        const bool le = q1 <= q2;
+        const bool ra = le && q1 < q3;
+        const bool rb = !le && q2 < q3;
+        const bool fa = ra ? f3 : f1, fb = rb ? f3 : f2;
+        const int ka = ra ? 0 : 2, kb = rb ? 0 : 1;     // candidate p1 <-> axis z, p2 <-> y, p3 <-> x
+        const int k3 = 3 - ka - kb;
+        const bool same = fa == fb;
+        const int kf = fa ? ka : kb, kn = fa ? kb : ka;
+        oe0 = same ? (fa ? 15 : 12) + k3 : 12 + kf;
+        oe1 = same ? 18 : 15 + kn;
+        near2 = same && !fa; far2 = same && fa;
+    }
+    e0 = tet ? te0 : oe0;
+    e1 = tet ? te1 : oe1;
+    T000 = (r0 || (!tet && near2)) ? LIVE : DEAD;
+    T111 = (r1 || (!tet && far2)) ? LIVE : DEAD;
+    // m = 1 corners (axis k): live in tet0 and the octahedron, in tet1 only as the case-B extra
+    T100 = (!r1 || opt0) ? LIVE : DEAD;
+    T010 = (!r1 || opt1) ? LIVE : DEAD;
+    T001 = (!r1 || opt2) ? LIVE : DEAD;
+    // m = 2 corners (omitting axis k): live in tet1 and the octahedron, in tet0 only as the case-B extra
+    T011 = (!r0 || opt0) ? LIVE : DEAD;
+    T101 = (!r0 || opt1) ? LIVE : DEAD;
+    T110 = (!r0 || opt2) ? LIVE : DEAD;
+}
+
+// x,y,z: lattice-space coordinates (vertex * octave frequency).  Returns noise3d * 103.
+NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_t lane4)
+{
+    const float MAGIC = 12582912.0f;   // 1.5 * 2^23: (x + MAGIC) - MAGIC rounds to nearest integer
+    const float so = (x + y + z) * (-1.0f / 6.0f);
+    const float xs = x + so, ys = y + so, zs = z + so;
+    const float tx = xs + MAGIC, ty = ys + MAGIC, tz = zs + MAGIC;
+    float bx = tx - MAGIC, by = ty - MAGIC, bz = tz - MAGIC;
+    // floor = round-to-nearest, minus 1 where that rounded up (opensimplex.py:18-21)
+    const bool ux = bx > xs, uy = by > ys, uz = bz > zs;
+    bx = ux ? bx - 1.0f : bx; by = uy ? by - 1.0f : by; bz = uz ? bz - 1.0f : bz;
+    NxfCtx c;
+    c.sm = sm; c.lane4 = lane4;
+    // low mantissa bits of (x + MAGIC) are the integer; only bits 0..7 survive the masks
+    c.xb7 = (nxf_as_uint(tx) - (ux ? 1u : 0u)) << 7;
+    c.yb7 = (nxf_as_uint(ty) - (uy ? 1u : 0u)) << 7;
+    c.zb7 = (nxf_as_uint(tz) - (uz ? 1u : 0u)) << 7;
+    const float fx = xs - bx, fy = ys - by, fz = zs - bz;
+    const float fsum = fx + fy + fz;
+    // position relative to the cell origin: f + fsum/3 (the un-skew of the in-cell coordinates;
+    // the reference's x - xb, opensimplex.py:283-297, is the same quantity)
+    c.dx0 = nxf_fma(fsum, 1.0f / 3.0f, fx);
+    c.dy0 = nxf_fma(fsum, 1.0f / 3.0f, fy);
+    c.dz0 = nxf_fma(fsum, 1.0f / 3.0f, fz);
+    c.v = 0.0f;
+
+    // ---- selection: live constants of the 8 cube corners + two extra codes ------------------
+    float T000, T100, T010, T001, T110, T101, T011, T111;
+    int e0, e1;
+#ifdef NXF_SELECT_BRANCHY
+    nxf_select_branchy(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
+#else
+    nxf_select(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
+#endif
 
     // ---- the 8 cube corners: shared hash tree (2 + 4 lookups), then one leaf each -----------
     const uint32_t hx0 = nxf_hash(c, c.xb7), hx1 = nxf_hash(c, c.xb7 + NXF_ROW);

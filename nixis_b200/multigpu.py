@@ -298,22 +298,24 @@ def run_multi_gpu_bench(args, rank, world, local):
         if timed is not None:
             timed.append(e)
 
+    sampler = B.ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = B.ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count
     timed = []
     t0, t1 = ev(), ev()
     torch.cuda.synchronize()
     dist.barrier()
+    sampler.mark_begin()
     t0.record()
     for _ in range(args.steps):
         step(timed)
     t1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     dist.barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count - launches0

@@ -86,4 +86,4 @@ def make_bool_elevation_mask(height, mask_elevation):
     if isinstance(height, torch.Tensor):
         return rt.mask_le(height, float(mask_elevation))
     h = rt.upload_f32(height)
-    return rt.mask_le(h, float(mask_elevation)).cpu().numpy().view(np.bool_)
+    return rt._to_host(rt.mask_le(h, float(mask_elevation))).view(np.bool_)

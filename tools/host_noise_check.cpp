@@ -23,6 +23,24 @@ int main(int argc, char **argv)
     }
     std::vector<char> sm(NXF_SMEM_BYTES);
     nxf_build_tables(perm8, grad8, sm.data(), 0, 1);
+    {   // branch-free selection == literal selection, exactly, including ties
+        std::mt19937_64 r2(11);
+        std::uniform_real_distribution<float> U01(0.0f, 1.0f);
+        long n = 0, bad = 0;
+        auto check = [&](float fx, float fy, float fz) {
+            float fsum = fx + fy + fz;
+            float A[8], B[8]; int a0, a1, b0, b1;
+            nxf_select_branchy(fx, fy, fz, fsum, A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], a0, a1);
+            nxf_select(fx, fy, fz, fsum, B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], b0, b1);
+            bool ok = a0 == b0 && a1 == b1;
+            for (int i = 0; i < 8; ++i) ok = ok && A[i] == B[i];
+            ++n; if (!ok) { if (bad < 5) printf("  MISMATCH f=(%g %g %g) e=(%d,%d) vs (%d,%d)\n", fx, fy, fz, a0, a1, b0, b1); ++bad; }
+        };
+        for (int i = 0; i < 4000000; ++i) check(U01(r2), U01(r2), U01(r2));
+        const float grid[] = {0.0f, 0.125f, 0.25f, 1.0f / 3.0f, 0.375f, 0.5f, 0.625f, 2.0f / 3.0f, 0.75f, 0.875f, 0.99999994f};
+        for (float x : grid) for (float y : grid) for (float z : grid) check(x, y, z);
+        printf("selection: %ld cases, %ld mismatches\n", n, bad);
+    }
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-1, 1);
     const double scales[] = {1.5, 9.4, 58.6, 366.2, 915.5, 5722.0, 35763.0};
