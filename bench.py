@@ -49,6 +49,21 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(key, metric_prefix="dram__bytes"):
+    """DRAM bytes per launch (read + write) of a kernel from the committed ncu --set full summary
+    (profiles/r01_ncu_summary.json, captured offline at the same d=2500 configuration), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    try:
+        d = json.load(open(p))[key]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            val, unit = d[name].split()
+            tot += float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -278,7 +293,10 @@ def run_ours(args):
     ero_gbs = BYTES_PER_VERT_ITER * V / (ero_launch_ms * 1e-3) / 1e9
     fbm_tflops = FLOP_PER_VERT_OCT * V * n_oct / (fbm_ms * 1e-3) / 1e12
     roofline = {"kernel": "erode3_plan_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ero_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "frac": ero_gbs / hbm_peak,
+                "traffic": ncu_traffic("r1c_erode3_v3_plan_d2500") if k == 2500 else None,
+                "traffic_source": "profiles/r01_ncu_summary.json (ncu --set full, same kernel, d=2500, bytes per launch)",
+                "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_VERT_ITER * V, "avg_launch_ms": ero_launch_ms}
     fbm_obj = {"value": V * n_oct / (fbm_ms * 1e-3) / 1e6, "unit": "Mvert*octaves/s", "ms": fbm_ms,
                "roofline": {"kernel": "fbm3_fast_kernel", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
@@ -353,7 +371,7 @@ def run_e2e(args, pipe, np, torch, rt, terrain, util, erosion):
     return {"value": V * (n_oct + iters) / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "api": "nixis_b200.terrain.sample_octaves / util.rescale / power_rescale / erosion.erode_terrain3 "
-                   "with float64 numpy arrays (points / neighbours pinned, intermediate heights pageable as numpy returns them)"}
+                   "with float64 numpy arrays (points / neighbours in pinned memory; every returned array is backed by pinned memory too)"}
 
 
 def main():
