@@ -267,6 +267,19 @@ class ShardedTerrain:
         h = self.fbm(out=out, minmax=mm)
         return assemble_heights(h, coll=self.coll, mm=mm)
 
+    def run_from_host(self, points_host, n_sweeps, out_host, world_radius=1.0):
+        """End-to-end step of this rank with HOST buffers: `points_host` float64 [n_own,3] (this rank's
+        slice of the reference's `points`, radius-scaled), `out_host` float64 [n_own] receives the
+        eroded heights.  H2D of the positions and D2H of the result happen here, every call."""
+        xyz = rt.xyz_from_f64(rt.upload(points_host), 1.0 / float(world_radius))
+        mm = rt.new_minmax(self.device)
+        h = rt.fbm3(self.tables, xyz, self.freq, self.amp, minmax=mm)
+        h, _, _ = assemble_heights(h, coll=self.coll, mm=mm)
+        self.erosion.load(h)
+        self.erosion.run(n_sweeps)
+        self.erosion.finish()
+        return rt.download_f64(self.erosion.heights.contiguous(), out=out_host)
+
 
 # ---------------------------------------------------------------------------------------------
 def run_multi_gpu_bench(args, rank, world, local):
@@ -329,6 +342,27 @@ def run_multi_gpu_bench(args, rank, world, local):
     dist.all_reduce(halo, op=dist.ReduceOp.MAX)
     nonfinite = torch.tensor([int((~torch.isfinite(ero.heights)).sum().item())], dtype=torch.int64, device=terr.device)
     dist.all_reduce(nonfinite)
+    # ---- end to end with host buffers: every rank uploads its slice of `points`, downloads its heights
+    e2e = None
+    if not args.no_e2e:
+        import time
+        pts = torch.empty((n_own, 3), dtype=torch.float64, pin_memory=True)
+        pts.copy_(rt.mesh_points(k, terr.begin, terr.end, f32=False, f64=True)[1])
+        out_h = torch.empty(n_own, dtype=torch.float64, pin_memory=True)
+        pts_np, out_np = pts.numpy(), out_h.numpy()
+        terr.run_from_host(pts_np, iters, out_np)            # warm-up
+        torch.cuda.synchronize(); dist.barrier()
+        reps = max(1, min(2, args.steps))
+        t_0 = time.perf_counter()
+        for _ in range(reps):
+            terr.run_from_host(pts_np, iters, out_np)
+        torch.cuda.synchronize(); dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t_0) / reps], dtype=torch.float64, device=terr.device)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": V * (n_oct + iters) / dt.item() / 1e6, "unit": B.UNIT, "ms_per_step": dt.item() * 1e3,
+               "h2d_bytes_per_step": int(V * 24), "d2h_bytes_per_step": int(V * 8),
+               "api": "nixis_b200.multigpu.ShardedTerrain.run_from_host: every rank uploads its float64 slice of "
+                      "`points` from pinned memory and downloads its float64 heights (bytes summed over ranks)"}
     if rank != 0:
         return
     value = V * (n_oct + iters) / (ms_per_step * 1e-3) / 1e6
@@ -349,4 +383,6 @@ def run_multi_gpu_bench(args, rank, world, local):
                          "traffic": None, "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": B.BYTES_PER_VERT_ITER * n_own, "avg_launch_ms": ero_launch_ms},
             "clocks": clocks, "gpu_launches": launches}
+    if e2e is not None:
+        line["e2e"] = e2e
     print(json.dumps(line))
