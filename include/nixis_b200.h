@@ -72,6 +72,14 @@ int nxb_noise4_f32(void *tables, const float *x, const float *y, const float *z,
 int nxb_fbm3_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
                  const double *freq_host, const double *amp_host,
                  const float *init, float *out, float *minmax, void *stream);
+/* Reference-exact mode of the same function: IEEE double, no FMA contraction, the reference's
+ * operation order -> bit-identical to the numba output for the same float64 vertices.
+ * verts: double[n][3] (device), multiplied by `scale` first (nixis.py:249 `points *= world_radius`;
+ * pass 1.0 for vertices that are already radius-scaled); nr_host[o] = n_freq_o / world_radius,
+ * ns_host[o] = n_amp_o / world_radius (terrain.py:43); out = init + sum_o (e+1)*0.5*ns*radius. */
+int nxb_fbm3_f64(void *tables, const double *verts, int64_t n, int n_oct,
+                 const double *nr_host, const double *ns_host, double radius, double scale,
+                 const double *init, double *out, void *stream);
 /* 4-D variant (no reference driver exists; w coordinate = w_host[o] per octave). */
 int nxb_fbm4_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
                  const double *freq_host, const double *amp_host, const double *w_host,
@@ -166,6 +174,12 @@ int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, cons
                                   uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
                                   void *ticket, const int32_t *tile_order /* nullable: processing order */,
                                   void *stream);
+/* Reference-exact mode of the sweep: float64 positions / state, no FMA, the reference's operation and
+ * neighbour order -> bit-identical to erosion_iteration3 (erosion.py:197-279) preceded by
+ * `water += rain` (erosion.py:182-183).  nodes: double[.][3]; ping-pong buffers of n doubles. */
+int nxb_erode3_step_f64(const double *nodes, const int32_t *adj,
+                        const double *h_in, const double *w_in, const double *s_in,
+                        double *h_out, double *w_out, double *s_out, int64_t n, double rain, void *stream);
 /* erosion.py:76-99 erosion_iteration1 */
 int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
                         int64_t v_begin, int64_t v_end, void *stream);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "nxb_noise2_f32": (_i, [_p, _p, _p, _i64, _p, _p]),
     "nxb_noise4_f32": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p]),
     "nxb_fbm3_f32": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "nxb_fbm3_f64": (_i, [_p, _p, _i64, _i, _p, _p, _d, _d, _p, _p, _p]),
     "nxb_fbm4_f32": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "nxb_mask_le_f32": (_i, [_p, _i64, _f, _p, _p]),
     "nxb_mesh_icosa_points": (_i, [_i, _i64, _i64, _p, _p, _p]),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
     "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
                                            _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _p]),
+    "nxb_erode3_step_f64": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _d, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "nxb_halo_put_f32": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
     "nxb_halo_wait": (_i, [_p, _p, _i, C.c_uint32, _p]),

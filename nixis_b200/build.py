@@ -10,7 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libnixis_b200.so")
 SOURCES = ["nxb_api.cu", "nxb_noise.cu", "nxb_mesh.cu", "nxb_adjacency.cu", "nxb_assembly.cu",
-           "nxb_erosion.cu", "nxb_halo.cu"]
+           "nxb_erosion.cu", "nxb_halo.cu", "nxb_noise_f64.cu"]
+# per-file extra flags: the reference-exact FP64 kernels must not contract a*b+c into FMA
+EXTRA_FLAGS = {"nxb_noise_f64.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "-DNXB_HAVE_NOISE4"] + (["-DNXB_ERO_DEBUG_WAIT"] if os.environ.get("NXB_ERO_DEBUG_WAIT") else [])
 
@@ -41,7 +43,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + EXTRA_FLAGS.get(os.path.basename(s), []) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             logs.append(r.stderr)
             if r.returncode != 0:

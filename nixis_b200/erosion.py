@@ -81,8 +81,37 @@ class Erosion3State:
         return self.cur[2][: self.n]
 
 
-def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbose=True, return_state=False):
-    """erosion.py:172-192.  `heights` (numpy float64) is eroded IN PLACE and None is returned;
+def _erode_terrain3_exact(nodes, neighbors, heights, num_iter, return_state):
+    """float64, no FMA, reference order: bit-identical to the reference (nxb_erode3_step_f64)."""
+    import ctypes as C
+    from . import _lib
+    adj = _neighbors(neighbors)
+    if isinstance(nodes, DeviceMesh):
+        n64 = rt.mesh_points(nodes.k, nodes.v_begin, nodes.v_begin + nodes.n_vertices, f32=False, f64=True,
+                             device=nodes.xyz.device)[1] * nodes.radius
+    elif isinstance(nodes, torch.Tensor):
+        n64 = nodes
+    else:
+        n64 = rt.upload(np.ascontiguousarray(nodes, dtype=np.float64))
+    dev_io = isinstance(heights, torch.Tensor)
+    cur = [heights.clone() if dev_io else rt.upload(np.ascontiguousarray(heights, dtype=np.float64)), None, None]
+    cur[1], cur[2] = torch.zeros_like(cur[0]), torch.zeros_like(cur[0])
+    nxt = [torch.empty_like(t) for t in cur]
+    for _ in range(num_iter):
+        _lib.call("nxb_erode3_step_f64", rt._ptr(n64), rt._ptr(adj), rt._ptr(cur[0]), rt._ptr(cur[1]), rt._ptr(cur[2]),
+                  rt._ptr(nxt[0]), rt._ptr(nxt[1]), rt._ptr(nxt[2]), cur[0].numel(), C.c_double(RAIN_AMOUNT), rt._stream())
+        cur, nxt = nxt, cur
+    if dev_io:
+        return tuple(cur) if return_state else cur[0]
+    heights[...] = rt._to_host(cur[0])
+    if return_state:
+        return rt._to_host(cur[1]), rt._to_host(cur[2])
+    return None
+
+
+def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbose=True, return_state=False, exact=False):
+    """erosion.py:172-192.  exact=True: float64 kernel without FMA in the reference's operation order,
+    bit-identical to the reference (slower: double state, global gathers); default FP32 tile-plan kernel.  `heights` (numpy float64) is eroded IN PLACE and None is returned;
     with CUDA tensors the new height tensor is returned.  water / sediment start at zero and are
     discarded unless return_state=True.  `snapshot` (per-iteration PNG export) is outside the hot
     path and not supported."""
@@ -92,6 +121,8 @@ def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbos
         print("Starting terrain erosion...")
     if num_iter <= 0:
         num_iter = 1
+    if exact:
+        return _erode_terrain3_exact(nodes, neighbors, heights, num_iter, return_state)
     adj = _neighbors(neighbors)
     dev_io = isinstance(heights, torch.Tensor)
     h32 = heights if dev_io else rt.upload_f32(heights)

@@ -103,6 +103,23 @@ def fbm3(tables, xyz, freq, amp, init=None, out=None, minmax=None):
     return out
 
 
+def fbm3_exact(tables, verts64, n_octaves, n_init_roughness, n_init_strength, n_roughness, n_persistence,
+               world_radius, scale=1.0, init=None):
+    """Reference-exact float64 fBm (nxb_fbm3_f64): verts64 float64 [n,3] CUDA, returns float64 [n] CUDA."""
+    n = verts64.shape[0]
+    nr, ns = [], []
+    f, a = n_init_roughness, n_init_strength          # Python floats, advanced like terrain.py:44-45
+    for _ in range(int(n_octaves)):
+        nr.append(f / world_radius)
+        ns.append(a / world_radius)
+        f *= n_roughness
+        a *= n_persistence
+    out = torch.empty(n, dtype=torch.float64, device=verts64.device)
+    _lib.call("nxb_fbm3_f64", C.c_void_p(tables.handle), _ptr(verts64), n, len(nr), _dbl(nr), _dbl(ns),
+              C.c_double(world_radius), C.c_double(scale), _ptr(init), _ptr(out), _stream())
+    return out
+
+
 def fbm4(tables, xyz, freq, amp, w, init=None, out=None, minmax=None):
     n = xyz.shape[0]
     if out is None:

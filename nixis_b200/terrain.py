@@ -32,9 +32,16 @@ def _is_device(v):
 
 
 def sample_octaves(verts, elevations, perm, pgi, n_octaves=1, n_init_roughness=1.5, n_init_strength=0.4,
-                   n_roughness=2.0, n_persistence=0.5, world_radius=1.0, verbose=True, minmax=None):
-    """Sample octaves of noise and combine them together (terrain.py:32-59)."""
+                   n_roughness=2.0, n_persistence=0.5, world_radius=1.0, verbose=True, minmax=None, exact=False):
+    """Sample octaves of noise and combine them together (terrain.py:32-59).
+
+    exact=False (default): FP32 throughput kernel, result within 1e-5 of the range of the reference's.
+    exact=True: float64 kernel without FMA contraction in the reference's operation order -- the
+    result is BIT-IDENTICAL to the reference's for the same float64 vertices (about 4x slower)."""
     t0 = time.perf_counter()
+    if exact:
+        return _sample_octaves_exact(verts, elevations, perm, pgi, n_octaves, n_init_roughness, n_init_strength,
+                                     n_roughness, n_persistence, world_radius)
     # the kernel works on unit-sphere float positions; nr = freq/world_radius applied to the
     # radius-scaled verts (terrain.py:17,43) is the same lattice coordinate
     xyz, fscale = _device_xyz(verts, 1.0 / float(world_radius))
@@ -59,6 +66,32 @@ def sample_octaves(verts, elevations, perm, pgi, n_octaves=1, n_init_roughness=1
     if elevations is not None:               # in place, like `elevations +=` (terrain.py:43)
         return rt.download_f64(out, out=elevations)
     return rt.download_f64(out)
+
+
+def _sample_octaves_exact(verts, elevations, perm, pgi, n_octaves, f0, a0, roughness, persistence, world_radius):
+    tables = rt.tables_for(perm, pgi)
+    scale = 1.0
+    if isinstance(verts, DeviceMesh):
+        # the mesh holds unit-sphere positions; nixis.py:249 scales them by the radius first
+        v64 = rt.mesh_points(verts.k, verts.v_begin, verts.v_begin + verts.n_vertices, f32=False, f64=True,
+                             device=verts.xyz.device)[1]
+        scale = verts.radius
+    elif isinstance(verts, torch.Tensor):
+        assert verts.dtype == torch.float64 and verts.shape[1] == 3, "exact mode needs float64 [n,3] positions"
+        v64 = verts
+    else:
+        v64 = rt.upload(np.ascontiguousarray(verts, dtype=np.float64))
+    init = None
+    if elevations is not None:
+        init = elevations if isinstance(elevations, torch.Tensor) else rt.upload(np.ascontiguousarray(elevations, dtype=np.float64))
+    out = rt.fbm3_exact(tables, v64, n_octaves, f0, a0, roughness, persistence, float(world_radius), scale, init)
+    if _is_device(verts) or isinstance(elevations, torch.Tensor):
+        return out
+    host = rt._to_host(out)
+    if elevations is not None:
+        elevations[...] = host
+        return elevations
+    return host
 
 
 def sample_octaves4(verts, elevations, perm, n_octaves=1, n_init_roughness=1.5, n_init_strength=0.4,

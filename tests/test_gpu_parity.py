@@ -120,6 +120,29 @@ def test_sample_octaves_vs_reference_golden(nx, golden):
         assert h.dtype == np.float64 and relerr(h, g[tag]) <= tol, (tag, relerr(h, g[tag]))
 
 
+def test_sample_octaves_exact_mode_bit_identical(nx, golden):
+    """exact=True: float64, no FMA, reference operation order -> bit-identical to the reference's output
+    (every golden fBm case, incl. Earth radius, 12 octaves and the accumulate-in-place call)."""
+    g = golden("fbm")
+    for k, s, o, R in g["cases"]:
+        k, s, o = int(k), int(s), int(o)
+        pts, _ = icosphere.icosa_sphere(k)
+        perm, pgi = nx.osi.init(s)
+        h = nx.terrain.sample_octaves(pts * R, None, perm, pgi, o, 1.5, 0.4, 2.5, 0.5, R, verbose=False, exact=True)
+        tag = f"k{k}_s{s}_o{o}_{'earth' if R != 1.0 else 'unit'}"
+        assert h.dtype == np.float64 and np.array_equal(h, g[tag]), tag
+    pts, _ = icosphere.icosa_sphere(8)
+    perm, pgi = nx.osi.init(7)
+    e = np.linspace(-1, 1, len(pts))
+    r = nx.terrain.sample_octaves(pts, e, perm, pgi, 3, 2.0, 0.7, 2.0, 0.45, 1.0, verbose=False, exact=True)
+    assert r is e and np.array_equal(e, g["k8_s7_accum"])
+    # device mesh (closed-form float64 positions) == numpy positions
+    mesh = nx.util.create_mesh(32, device=True, verbose=False)
+    perm, pgi = nx.osi.init(12345)
+    hd = nx.terrain.sample_octaves(mesh, None, perm, pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0, verbose=False, exact=True)
+    assert np.array_equal(hd.cpu().numpy(), g["k32_s12345_o8_unit"])
+
+
 def test_sample_octaves_accumulates_in_place(nx, golden):
     g = golden("fbm")
     pts, _ = icosphere.icosa_sphere(8)
@@ -330,6 +353,24 @@ def test_erosion3_vs_reference_golden(nx, golden, k, seed, R, steps):
         h = h0.copy()
         assert nx.erosion.erode_terrain3(nodes, adj, h, num_iter=11, verbose=False) is None
         assert relerr(h, g[f"{t}_driver11_h"]) <= 1e-4
+
+
+@pytest.mark.parametrize("k,seed,R,steps", [(8, 12345, 1.0, (1, 5, 11, 50)), (32, 12345, 1.0, (1, 5, 11, 50)),
+                                            (32, 0, EARTH_R, (1, 3, 5))])
+def test_erosion3_exact_mode_bit_identical(nx, golden, k, seed, R, steps):
+    """exact=True: float64 / no FMA / reference order -> heights, water and sediment bit-identical to the
+    reference after every recorded number of sweeps (incl. the diverging Earth-radius trajectory)."""
+    g = golden("erosion")
+    pts, cells = icosphere.icosa_sphere(k)
+    nodes = pts * R
+    adj = nx.util.build_adjacency(cells)
+    nx.util.sort_adjacency(adj)
+    t = f"k{k}_s{seed}_{'earth' if R != 1.0 else 'unit'}"
+    for n in steps:
+        h = g[f"{t}_h0"].copy()
+        w, s = nx.erosion.erode_terrain3(nodes, adj, h, num_iter=n, verbose=False, return_state=True, exact=True)
+        assert np.array_equal(h, g[f"{t}_it3_n{n}_h"]), n
+        assert np.array_equal(w, g[f"{t}_it3_n{n}_w"]) and np.array_equal(s, g[f"{t}_it3_n{n}_s"]), n
 
 
 @pytest.mark.parametrize("k,seed,R", [(8, 12345, 1.0), (32, 12345, 1.0), (32, 0, EARTH_R)])
