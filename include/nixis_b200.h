@@ -97,6 +97,17 @@ int nxb_mesh_icosa_cells(int k, int64_t t_begin, int64_t t_end, int32_t *cells, 
 /* double[n][3] * scale -> float4 (used to ingest caller-supplied float64 vertices) */
 int nxb_xyz_f64_to_f32(const double *xyz_f64, int64_t n, double scale, nxb_float4 *xyz_f32, void *stream);
 
+/* ---- util.py: equirectangular export --------------------------------------- */
+/* util.py:290-308 make_ll_arr: xyz (double[height][width][3]) of every pixel's lat/lon */
+int nxb_ll_grid_f64(int width, int height, double radius, double *xyz_out, void *stream);
+/* The 3 nearest vertices of the k-division icosphere (radius-scaled) to each query position --
+ * what the reference gets from scipy KDTree(points).query(ll, k=3) (nixis.py:270-283), found
+ * analytically from the closed-form mesh.  dists double[n][3] ascending, ids int64[n][3]. */
+int nxb_ico_nearest3_f64(int k, double radius, const double *query_xyz, int64_t n, double *dists, int64_t *ids, void *stream);
+/* util.py:343-367 make_gray_array: inverse-distance blend, float64, reference operation order,
+ * int() truncation.  colors: double[V]; out int32[n]. */
+int nxb_idw_gray_f64(const double *dists, const int64_t *ids, const double *colors, int64_t n, int32_t *out, void *stream);
+
 /* ---- util.py: adjacency -------------------------------------------------- */
 /* util.py:591-613 build_adjacency.  cells int32[T][3]; adj int32[V][6], -1 padded.
  * workspace: device scratch of nxb_adj_build_workspace(V) bytes.  Deterministic

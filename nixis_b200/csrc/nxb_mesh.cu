@@ -230,3 +230,159 @@ NXB_API int nxb_xyz_f64_to_f32(const double *xyz_f64, int64_t n, double scale, n
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
+
+// =================================================================================================
+// Equirectangular export (util.py:290-308, 343-367; nixis.py:270-302).
+//
+// The reference builds a scipy KD-tree over all vertices (26 s at k=2500, nixis.py:268-269) and asks
+// it for the 3 nearest vertices of every pixel direction.  On the closed-form icosphere the same
+// answer comes from arithmetic: find the icosahedron face(s) whose cone contains the direction,
+// convert to the face's barycentric grid, and compare exact FP64 distances to the 4x4 window of grid
+// nodes around it (plus the windows of neighbouring faces when the direction is within 1.5 grid
+// steps of a face edge).  Checked against scipy.spatial.KDTree in tests/test_gpu_export.py.
+
+// util.py:290-308 make_ll_arr + :79-88 latlon2xyz: xyz of every pixel of a width x height
+// equirectangular map (row 0 = north pole; the longitude of the last column stops one step short of
+// +180, util.py:298-299).
+__global__ void __launch_bounds__(256)
+ll_grid_kernel(int width, int height, double radius, double *__restrict__ out)
+{
+    const double latpercent = 180.0 / (double)(height - 1), lonpercent = 360.0 / (double)width;
+    const double D2R = 3.141592653589793 / 180;
+    const int64_t n = (int64_t)width * height;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i / width), w = (int)(i % width);
+        // every product / sum rounded once, in the reference's order (no FMA contraction)
+        const double lat = fmax(__dsub_rn(90.0, __dmul_rn((double)h, latpercent)), -90.0);
+        const double lon = fmax(__dadd_rn(-180.0, __dmul_rn((double)w, lonpercent)), -180.0);
+        const double rl = __dmul_rn(lat, D2R), ro = __dmul_rn(lon, D2R);
+        const double rc = __dmul_rn(radius, cos(rl));
+        out[3 * i] = __dmul_rn(rc, cos(ro));
+        out[3 * i + 1] = __dmul_rn(rc, sin(ro));
+        out[3 * i + 2] = __dmul_rn(radius, sin(rl));
+    }
+}
+
+NXB_API int nxb_ll_grid_f64(int width, int height, double radius, double *xyz_out, void *stream)
+{
+    NXB_ARG(width >= 1 && height >= 2 && xyz_out);
+    const int64_t n = (int64_t)width * height;
+    ll_grid_kernel<<<nxb_grid_resident(ll_grid_kernel, 256, 0, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(width, height, radius, xyz_out);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
+__device__ __forceinline__ void top3_insert(double d2, int32_t id, double (&bd)[3], int32_t (&bi)[3])
+{
+    if (id == bi[0] || id == bi[1] || id == bi[2]) return;      // the same vertex seen from two faces
+    if (d2 < bd[2]) {
+        if (d2 < bd[1]) {
+            bd[2] = bd[1]; bi[2] = bi[1];
+            if (d2 < bd[0]) { bd[1] = bd[0]; bi[1] = bi[0]; bd[0] = d2; bi[0] = id; }
+            else { bd[1] = d2; bi[1] = id; }
+        } else { bd[2] = d2; bi[2] = id; }
+    }
+}
+
+// query: double[n][3] positions (any radius > 0); out: dists double[n][3] ascending, ids int64[n][3]
+__global__ void __launch_bounds__(256)
+ico_nearest3_kernel(int k, double radius, const double *__restrict__ query, int64_t n_q,
+                    double *__restrict__ dists, long long *__restrict__ ids)
+{
+    __shared__ double s_inv[20][9];
+    if (threadIdx.x < 20) {         // rows of M^-1 for M = [c0 c1 c2]: (c1 x c2, c2 x c0, c0 x c1) / det
+        const int f = threadIdx.x;
+        const double *a = c_corner[c_face[f][0]], *b = c_corner[c_face[f][1]], *c = c_corner[c_face[f][2]];
+        const double bc[3] = {b[1] * c[2] - b[2] * c[1], b[2] * c[0] - b[0] * c[2], b[0] * c[1] - b[1] * c[0]};
+        const double ca[3] = {c[1] * a[2] - c[2] * a[1], c[2] * a[0] - c[0] * a[2], c[0] * a[1] - c[1] * a[0]};
+        const double ab[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        const double det = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2];
+        for (int q = 0; q < 3; ++q) { s_inv[f][q] = bc[q] / det; s_inv[f][3 + q] = ca[q] / det; s_inv[f][6 + q] = ab[q] / det; }
+    }
+    __syncthreads();
+    const int64_t n = k;
+    const double margin = 1.5 / (double)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += (int64_t)gridDim.x * blockDim.x) {
+        const double qx = query[3 * i], qy = query[3 * i + 1], qz = query[3 * i + 2];
+        const double qn = sqrt(qx * qx + qy * qy + qz * qz);
+        const double ux = qx / qn, uy = qy / qn, uz = qz / qn;           // direction on the unit sphere
+        double bd[3] = {1e300, 1e300, 1e300};
+        int32_t bi[3] = {-1, -2, -3};
+        for (int f = 0; f < 20; ++f) {
+            const double *m = s_inv[f];
+            const double al = m[0] * ux + m[1] * uy + m[2] * uz, be = m[3] * ux + m[4] * uy + m[5] * uz,
+                         ga = m[6] * ux + m[7] * uy + m[8] * uz;
+            const double s = al + be + ga;
+            if (!(s > 0.0)) continue;
+            const double b0 = al / s, b1 = be / s, b2 = ga / s;           // barycentric on the flat face
+            if (fmin(b0, fmin(b1, b2)) < -margin) continue;
+            const int64_t i0 = (int64_t)floor(b2 * (double)n), j0 = (int64_t)floor(b1 * (double)n);
+            const double *c0 = c_corner[c_face[f][0]], *c1 = c_corner[c_face[f][1]], *c2 = c_corner[c_face[f][2]];
+            for (int64_t r = i0 - 1; r <= i0 + 2; ++r) {
+                if (r < 0 || r > n) continue;
+                for (int64_t c = j0 - 1; c <= j0 + 2; ++c) {
+                    if (c < 0 || r + c > n) continue;
+                    const double wi = (double)r / (double)n, wj = (double)c / (double)n, w0 = 1.0 - wi - wj;
+                    double px = w0 * c0[0] + wj * c1[0] + wi * c2[0], py = w0 * c0[1] + wj * c1[1] + wi * c2[1],
+                           pz = w0 * c0[2] + wj * c1[2] + wi * c2[2];
+                    const double inv = 1.0 / sqrt(px * px + py * py + pz * pz);
+                    px = px * inv - ux; py = py * inv - uy; pz = pz * inv - uz;
+                    top3_insert(px * px + py * py + pz * pz, face_node(n, f, r, c), bd, bi);
+                }
+            }
+        }
+        // exact distances to the mesh's own vertex positions (radius-scaled), then order by them
+        double dd[3];
+        for (int t = 0; t < 3; ++t) {
+            if (bi[t] < 0) { dd[t] = 1e300; continue; }
+            double x, y, z;
+            icosa_point(n, bi[t], x, y, z);
+            const double ax = qx - x * radius, ay = qy - y * radius, az = qz - z * radius;
+            dd[t] = sqrt(ax * ax + ay * ay + az * az);
+        }
+#define SWAP3(a, b) if (dd[b] < dd[a]) { double td = dd[a]; dd[a] = dd[b]; dd[b] = td; int32_t ti = bi[a]; bi[a] = bi[b]; bi[b] = ti; }
+        SWAP3(0, 1) SWAP3(1, 2) SWAP3(0, 1)
+#undef SWAP3
+        for (int t = 0; t < 3; ++t) { dists[3 * i + t] = dd[t]; ids[3 * i + t] = bi[t]; }
+    }
+}
+
+NXB_API int nxb_ico_nearest3_f64(int k, double radius, const double *query_xyz, int64_t n, double *dists, int64_t *ids, void *stream)
+{
+    NXB_ARG(k >= 1 && k <= 14000 && radius > 0.0 && n >= 0);
+    if (n == 0) return NXB_OK;
+    NXB_ARG(query_xyz && dists && ids);
+    ico_nearest3_kernel<<<nxb_grid_resident(ico_nearest3_kernel, 256, 0, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        k, radius, query_xyz, n, dists, (long long *)ids);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
+// util.py:343-367 make_gray_array: inverse-distance blend of the 3 nearest vertices' values,
+// float64, in the reference's operation order; int() truncation; out int32[n].
+__global__ void __launch_bounds__(256)
+idw_gray_kernel(const double *__restrict__ dists, const long long *__restrict__ ids, const double *__restrict__ colors,
+                int64_t n, int32_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double d0 = dists[3 * i], d1 = dists[3 * i + 1], d2 = dists[3 * i + 2];
+        const double sd = __dadd_rn(__dadd_rn(d0, d1), d2);
+        const double w0 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d0, 0.00001), sd)), w1 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d1, 0.00001), sd)),
+                     w2 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d2, 0.00001), sd));
+        const double t = __dadd_rn(__dadd_rn(w0, w1), w2);
+        const double v = __dadd_rn(__dadd_rn(__dmul_rn(colors[ids[3 * i]], __ddiv_rn(w0, t)), __dmul_rn(colors[ids[3 * i + 1]], __ddiv_rn(w1, t))),
+                                   __dmul_rn(colors[ids[3 * i + 2]], __ddiv_rn(w2, t)));
+        out[i] = (int32_t)v;        // int(): truncation toward zero
+    }
+}
+
+NXB_API int nxb_idw_gray_f64(const double *dists, const int64_t *ids, const double *colors, int64_t n, int32_t *out, void *stream)
+{
+    NXB_ARG(n >= 0);
+    if (n == 0) return NXB_OK;
+    NXB_ARG(dists && ids && colors && out);
+    idw_gray_kernel<<<nxb_grid_resident(idw_gray_kernel, 256, 0, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        dists, (const long long *)ids, colors, n, out);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}

@@ -310,6 +310,31 @@ def scatter(src, idx, dst):
     _lib.call("nxb_scatter_f32", _ptr(src), _ptr(idx), idx.numel(), _ptr(dst), _stream())
 
 
+def ll_grid(width, height, radius):
+    """util.py:290-308: float64 [height, width, 3] CUDA tensor of pixel positions."""
+    require_cuda()
+    out = torch.empty((height, width, 3), dtype=torch.float64, device="cuda")
+    _lib.call("nxb_ll_grid_f64", int(width), int(height), C.c_double(radius), _ptr(out), _stream())
+    return out
+
+
+def ico_nearest3(k, radius, query64):
+    """query64: float64 [..., 3] CUDA -> (dists float64 [..., 3] ascending, ids int64 [..., 3])."""
+    n = query64.numel() // 3
+    dists = torch.empty(query64.shape, dtype=torch.float64, device=query64.device)
+    ids = torch.empty(query64.shape, dtype=torch.int64, device=query64.device)
+    _lib.call("nxb_ico_nearest3_f64", int(k), C.c_double(radius), _ptr(query64), n, _ptr(dists), _ptr(ids), _stream())
+    return dists, ids
+
+
+def idw_gray(dists, ids, colors64):
+    """util.py:343-367: int32 [...] blend of colors64 (float64 [V]) at the 3 nearest vertices."""
+    n = dists.numel() // 3
+    out = torch.empty(dists.shape[:-1], dtype=torch.int32, device=dists.device)
+    _lib.call("nxb_idw_gray_f64", _ptr(dists), _ptr(ids), _ptr(colors64), n, _ptr(out), _stream())
+    return out
+
+
 def to_f64(x32):
     out = torch.empty(x32.shape, dtype=torch.float64, device=x32.device)
     _lib.call("nxb_f32_to_f64", _ptr(x32), x32.numel(), _ptr(out), _stream())

@@ -1,9 +1,11 @@
 """Drop-in for the hot-path half of the reference's `util` module (util.py) on B200.
 
 Kept: `create_mesh`, `rescale`, `power_rescale`, `find_percent_val`, `build_adjacency`,
-`sort_adjacency` -- same names, argument order, defaults, return / in-place conventions.
-Everything else in the reference's util.py (image export, KD-tree, file I/O, lat/lon) is
-outside the hot path and is not provided here.
+`sort_adjacency` -- same names, argument order, defaults, return / in-place conventions -- and,
+from the "next" rows of SURVEY section 8f, the equirectangular export chain `make_ll_arr`,
+`build_KDTree` (+ `cfg.KDT.query`), `make_gray_array`, `build_image_data`.
+File I/O (save_image / save_mesh / settings), lat/lon helpers and memory pretty-printers are
+outside the path and not provided here.
 
 numpy in -> numpy out (float64 / int32, like the reference); `DeviceMesh` and CUDA tensors
 in -> CUDA tensors out (the resident path bench.py and the multi-GPU driver use).
@@ -14,6 +16,13 @@ import numpy as np
 import torch
 
 from . import runtime as rt
+
+try:                    # inside the reference tree: share the reference's globals (cfg.py:3-14)
+    import cfg
+    if not hasattr(cfg, "IMG_QUERY_DATA"):
+        raise ImportError
+except ImportError:
+    from . import cfg
 
 
 class DeviceMesh:
@@ -161,3 +170,105 @@ def sort_adjacency(adj):
     a = np.ascontiguousarray(adj, dtype=np.int32)
     adj[...] = rt.adj_sort(rt.upload(a)).cpu().numpy()
     return None
+
+
+# ---------------------------------------------------------------------------------------------
+# Equirectangular export: util.py:275-429, nixis.py:270-302, 382-389
+def make_ll_arr(width, height, radius):
+    """XYZ of each pixel's latitude / longitude (util.py:290-308): float64 [height, width, 3]."""
+    return rt._to_host(rt.ll_grid(width, height, radius))
+
+
+class IcoNearest:
+    """Stands in for scipy.spatial.KDTree over the icosphere's vertices (util.py:275-285,
+    nixis.py:279-283): `.query(x, k=3)` returns (distances, indices) of the 3 nearest vertices, found
+    analytically on the closed-form mesh instead of through a tree (26 s to build at k=2500)."""
+
+    def __init__(self, points):
+        if isinstance(points, DeviceMesh):
+            self.k, self.radius = points.k, points.radius
+            return
+        pts = np.asarray(points)
+        V = len(pts)
+        k = int(round(((V - 2) / 10.0) ** 0.5))
+        if 10 * k * k + 2 != V:
+            raise ValueError("build_KDTree: the analytic nearest-vertex search needs the k-division icosphere "
+                             f"(10k^2+2 vertices), got {V} points")
+        self.k = k
+        self.radius = float(np.linalg.norm(pts[0]))
+        # the points must BE the meshzoo-ordered icosphere: compare a sample with the closed form
+        probe = np.unique(np.linspace(0, V - 1, 64).astype(np.int64))
+        ref = rt.mesh_points(k, f32=False, f64=True)[1][torch.from_numpy(probe).cuda()].cpu().numpy() * self.radius
+        if not np.allclose(pts[probe], ref, rtol=1e-9, atol=1e-9 * self.radius):
+            raise ValueError("build_KDTree: points are not the meshzoo-ordered icosphere this library generates")
+
+    def query(self, x, k=3, workers=1, **_):
+        if k != 3:
+            raise NotImplementedError("only the k=3 query of nixis.py:283 is provided")
+        dev_io = isinstance(x, torch.Tensor)
+        q = x if dev_io else rt.upload(np.ascontiguousarray(x, dtype=np.float64))
+        d, i = rt.ico_nearest3(self.k, self.radius, q)
+        return (d, i) if dev_io else (rt._to_host(d), rt._to_host(i))
+
+
+def build_KDTree(points, lf=10):
+    """util.py:275-285: sets cfg.KDT (here an `IcoNearest`, no tree is built)."""
+    print("Building KD Tree...")
+    t0 = time.perf_counter()
+    cfg.KDT = IcoNearest(points)
+    print(f"KD built in {time.perf_counter() - t0 :.5f} sec")
+
+
+def make_gray_array(width, height, dists, nbrs, colors):
+    """Sample vertices and build a grayscale map (util.py:343-367): inverse-distance blend of the 3
+    nearest vertices, int() truncation, result cast back to the dtype of `colors`."""
+    dev_io = isinstance(dists, torch.Tensor)
+    d = dists if dev_io else rt.upload(np.ascontiguousarray(dists, dtype=np.float64))
+    i = nbrs if isinstance(nbrs, torch.Tensor) else rt.upload(np.ascontiguousarray(nbrs, dtype=np.int64))
+    if isinstance(colors, torch.Tensor):
+        c64, orig = colors.to(torch.float64), None
+    else:
+        colors = np.asarray(colors)
+        c64, orig = rt.upload(np.ascontiguousarray(colors.astype(np.float64))), colors.dtype
+    out = rt.idw_gray(d.reshape(height, width, 3), i.reshape(height, width, 3), c64)
+    if dev_io:
+        return out
+    return rt._to_host(out).astype(orig)
+
+
+def build_image_data(colors=None, width=None, height=None):
+    """Use the nearest-vertex query results to build the maps for export (util.py:369-429).
+    colors: dict name -> [array, mode].  Width / height default to the shape of cfg.IMG_QUERY_DATA
+    (the reference re-reads options.json, util.py:381-383)."""
+    print("Sampling verts for texture...")
+    dists, nbrs = cfg.IMG_QUERY_DATA[0], cfg.IMG_QUERY_DATA[1]
+    height = height or dists.shape[0]
+    width = width or dists.shape[1]
+    if not isinstance(colors, dict):
+        print("ERROR: Must pass a dict when saving out texture maps.")
+    result = {}
+    for key, container in colors.items():
+        array, mode = container[0], container[1]
+        if array.dtype in ('int8', 'uint8', 'bool_'):
+            colors[key] = [rescale(array.astype(np.float64), 0, 255), mode]
+        elif array.dtype in ('uint16', 'uint32'):
+            pass
+        else:
+            colors[key] = [rescale(array, 0, 255), mode]
+    d_dev = rt.upload(np.ascontiguousarray(dists, dtype=np.float64))
+    i_dev = rt.upload(np.ascontiguousarray(nbrs, dtype=np.int64))
+    for key, container in colors.items():
+        array, mode = container[0], container[1]
+        t0 = time.perf_counter()
+        if mode in ('gray', 'GRAY', 'grey', 'GREY'):
+            c64 = rt.upload(np.ascontiguousarray(np.asarray(array).astype(np.float64)))
+            pixels = rt._to_host(rt.idw_gray(d_dev.reshape(height, width, 3), i_dev.reshape(height, width, 3), c64))
+        else:
+            raise NotImplementedError("RGB maps (util.py:310-341) are not part of the export row built so far")
+        colors[key] = None
+        print(f"  {key} pixels built in   {time.perf_counter() - t0 :.5f} sec")
+        if array.dtype in ('float16', 'int32', 'uint32', 'float32', 'int64', 'uint64', 'float64'):
+            result[key] = pixels.astype('uint8')
+        else:
+            result[key] = pixels.astype(array.dtype)
+    return result

@@ -209,6 +209,32 @@ def gen_erosion():
     save("erosion.npz", **out)
 
 
+def gen_export():
+    """make_ll_arr -> scipy KDTree query (k=3) -> make_gray_array, reference code."""
+    from scipy.spatial import KDTree
+    out = {}
+    for k, R, W, H in ((16, EARTH_R, 64, 32), (8, 1.0, 36, 19)):
+        pts, _ = icosphere.icosa_sphere(k)
+        points = pts * R
+        ll = util.make_ll_arr(W, H, R)
+        dists, nbrs = KDTree(points, leafsize=10).query(ll, k=3)
+        perm, pgi = osi.init(12345)
+        raw = quiet(terrain.sample_octaves, points, None, perm, pgi, 7, 1.5, 0.4, 2.5, 0.5, R)
+        height = assembly(raw)[-1]
+        ocean = terrain.make_bool_elevation_mask(height, 0.0)
+        t = f"k{k}_{W}x{H}"
+        out[f"{t}_ll"], out[f"{t}_dists"], out[f"{t}_nbrs"], out[f"{t}_height"] = ll, dists, nbrs, height
+        # nixis.py:382-389 and util.py:393-404 dtype handling, then util.py:343-367
+        absolute = (util.rescale(height, -4000, 8850) + (32768 - util.find_percent_val(-4000, 8850, 55.0))).astype('uint16')
+        relative = (util.rescale(height, 0, 65535)).astype('uint16')
+        out[f"{t}_abs_src"], out[f"{t}_rel_src"] = absolute, relative
+        out[f"{t}_abs"] = util.make_gray_array(W, H, dists, nbrs, absolute)
+        out[f"{t}_rel"] = util.make_gray_array(W, H, dists, nbrs, relative)
+        out[f"{t}_height255"] = util.make_gray_array(W, H, dists, nbrs, util.rescale(height, 0, 255)).astype('uint8')
+        out[f"{t}_ocean"] = util.make_gray_array(W, H, dists, nbrs, util.rescale(ocean.astype(np.float64), 0, 255)).astype(ocean.dtype)
+    save("export.npz", **out)
+
+
 def main():
     print("reference:", REF)
     gen_init()
@@ -217,6 +243,7 @@ def main():
     gen_adjacency()
     gen_assembly()
     gen_erosion()
+    gen_export()
     # provenance
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         import numba
