@@ -18,14 +18,16 @@ def nx():
     return util, runtime, torch
 
 
-def _same_neighbours(dists, nbrs, rd, rn, scale):
-    """ids must agree wherever the reference distances are not tied (within 1e-9 relative)."""
+def _same_neighbours(dists, nbrs, rd, rn, scale, query, pts):
+    """The answer is valid iff the distances equal the reference's and the ids really are at those
+    distances; where several vertices are equidistant (4th tied with 3rd on symmetric pixels, poles)
+    scipy and the analytic search may name different ones, so ids are compared only off ties."""
     assert np.allclose(dists, rd, rtol=1e-12, atol=1e-12 * scale)
-    order_free = np.sort(nbrs, axis=-1) == np.sort(rn, axis=-1)
-    tied = (np.abs(rd[..., 1:] - rd[..., :-1]) < 1e-9 * scale).any(axis=-1)
-    assert (order_free.all(axis=-1) | tied).all()
-    exact = (nbrs == rn).all(axis=-1)
-    assert (exact | tied).all()
+    true_d = np.linalg.norm(query[..., None, :] - pts[nbrs], axis=-1)
+    assert np.allclose(true_d, dists, rtol=1e-12, atol=1e-12 * scale)
+    assert (np.diff(dists, axis=-1) >= 0).all()
+    same = (np.sort(nbrs, axis=-1) == np.sort(rn, axis=-1)).all(axis=-1)
+    assert same.mean() > 0.9, same.mean()       # the rest are exact distance ties (validated above)
 
 
 @pytest.mark.parametrize("k,R,W,H", [(16, EARTH_R, 64, 32), (8, 1.0, 36, 19)])
@@ -39,7 +41,7 @@ def test_export_chain_vs_reference_golden(nx, golden, k, R, W, H):
     util.build_KDTree(pts * R)
     dists, nbrs = util.cfg.KDT.query(g[f"{t}_ll"], k=3, workers=-1)       # nixis.py:283
     assert dists.dtype == np.float64 and nbrs.dtype == np.int64 and nbrs.shape == (H, W, 3)
-    _same_neighbours(dists, nbrs, g[f"{t}_dists"], g[f"{t}_nbrs"], R)
+    _same_neighbours(dists, nbrs, g[f"{t}_dists"], g[f"{t}_nbrs"], R, g[f"{t}_ll"], pts * R)
     # the blend, fed with the reference's own query result: bit-exact integers
     for src, ref in (("abs_src", "abs"), ("rel_src", "rel")):
         got = util.make_gray_array(W, H, g[f"{t}_dists"], g[f"{t}_nbrs"], g[f"{t}_{src}"])
@@ -63,7 +65,7 @@ def test_nearest3_vs_scipy_kdtree_large(nx):
     rd, rn = KDTree(pts, leafsize=10).query(ll, k=3, workers=-1)
     util.build_KDTree(pts)
     d, n = util.cfg.KDT.query(ll, k=3)
-    _same_neighbours(d, n, rd, rn, R)
+    _same_neighbours(d, n, rd, rn, R, ll, pts)
     # random directions as well (not only the lat/lon grid), incl. exact vertex positions
     rng = np.random.default_rng(3)
     q = rng.normal(size=(200000, 3))
@@ -71,7 +73,7 @@ def test_nearest3_vs_scipy_kdtree_large(nx):
     q[:1000] = pts[rng.integers(0, len(pts), 1000)]
     rd, rn = KDTree(pts, leafsize=10).query(q, k=3, workers=-1)
     d, n = util.cfg.KDT.query(q, k=3)
-    _same_neighbours(d, n, rd, rn, R)
+    _same_neighbours(d, n, rd, rn, R, q, pts)
     assert (d[:1000, 0] < 1e-6).all()
 
 
