@@ -107,6 +107,14 @@ int nxb_ico_nearest3_f64(int k, double radius, const double *query_xyz, int64_t 
 /* util.py:343-367 make_gray_array: inverse-distance blend, float64, reference operation order,
  * int() truncation.  colors: double[V]; out int32[n]. */
 int nxb_idw_gray_f64(const double *dists, const int64_t *ids, const double *colors, int64_t n, int32_t *out, void *stream);
+/* One export map per launch, straight from a device-resident field (nixis.py:349, 386-389, 417 ->
+ * util.py:393-429): colour = rescale(field, lower, upper) + add over the given [x_min, x_max]
+ * (util.py:143), truncated to uint16 first when quantize_u16 (".astype('uint16')", nixis.py:386,389),
+ * blended like make_gray_array and stored as uint8 / uint16 (out_bits).  field_kind 0 = float32[V],
+ * 1 = uint8[V] (masks). */
+int nxb_idw_map(const double *dists, const int64_t *ids, const void *field, int field_kind, int64_t n,
+                double x_min, double x_max, double lower, double upper, double add, int quantize_u16,
+                int out_bits, void *out, void *stream);
 
 /* ---- util.py: adjacency -------------------------------------------------- */
 /* util.py:591-613 build_adjacency.  cells int32[T][3]; adj int32[V][6], -1 padded.

@@ -37,6 +37,7 @@ SIGNATURES = {
     "nxb_ll_grid_f64": (_i, [_i, _i, _d, _p, _p]),
     "nxb_ico_nearest3_f64": (_i, [_i, _d, _p, _i64, _p, _p, _p]),
     "nxb_idw_gray_f64": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "nxb_idw_map": (_i, [_p, _p, _p, _i, _i64, _d, _d, _d, _d, _d, _i, _i, _p, _p]),
     "nxb_adj_build_workspace": (_i64, [_i64]),
     "nxb_adj_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_adj_sort": (_i, [_p, _p, _i64, _p]),

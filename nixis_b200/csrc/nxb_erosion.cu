@@ -142,9 +142,19 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         int32_t word = 0;                       // this lane's word of the 16-word descriptor
         bool halo_ready = a.comm.n_wait == 0;
         const int32_t *order = a.comm.tile_order;
+        // order lookups are batched: lane l holds the entry of iteration 32 b + l, the next batch is
+        // already in flight.  (One dependent __ldg per tile in front of the descriptor load made the
+        // producer latency-bound: +30% per sweep.)  tile_of is called with i = 0, 1, 2, ... in turn.
+        int32_t ord_cur = 0, ord_nxt = 0;
+        auto ord_load = [&](int64_t b) -> int32_t {
+            const int64_t i = b * 32 + lane;
+            return i < my_tiles ? __ldg(order + blockIdx.x + i * gridDim.x) : 0;
+        };
+        if (order) { ord_cur = ord_load(0); ord_nxt = ord_load(1); }
         auto tile_of = [&](int64_t i) -> int64_t {       // i-th tile of this CTA
-            const int64_t slot = blockIdx.x + i * gridDim.x;
-            return order ? (int64_t)__ldg(order + slot) : slot;
+            if (!order) return blockIdx.x + i * gridDim.x;
+            if (i > 0 && (i & 31) == 0) { ord_cur = ord_nxt; ord_nxt = ord_load((i >> 5) + 1); }
+            return (int64_t)__shfl_sync(0xffffffffu, ord_cur, (int)(i & 31));
         };
         int64_t tile = my_tiles > 0 ? tile_of(0) : 0;
         int64_t tile_next = my_tiles > 1 ? tile_of(1) : 0;

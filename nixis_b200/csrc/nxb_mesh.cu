@@ -376,6 +376,60 @@ idw_gray_kernel(const double *__restrict__ dists, const long long *__restrict__ 
     }
 }
 
+// One export map in one launch (nixis.py:349, 386-389, 417 feeding util.py:393-429): the per-vertex
+// colour of `build_image_data` is derived on the fly from the device-resident field,
+//     c = ((x - x_min) / x_range) * new_range + lower [+ add]        (util.py:143, FP64, same order)
+//     c = (double)(uint16)c  when quantize != 0                       (.astype('uint16') truncation)
+// and blended exactly like make_gray_array.  No V-sized temporary exists.  field_kind 0: float32
+// heights, 1: uint8 mask.  out_bits 8 / 16.
+struct IdwMapArgs {
+    const double *dists; const long long *ids; const void *field; int field_kind;
+    double x_min, x_range, new_range, lower, add; int quantize; int out_bits; void *out; int64_t n;
+};
+
+__global__ void __launch_bounds__(256)
+idw_map_kernel(const __grid_constant__ IdwMapArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double d0 = a.dists[3 * i], d1 = a.dists[3 * i + 1], d2 = a.dists[3 * i + 2];
+        double c[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const long long id = a.ids[3 * i + j];
+            const double x = a.field_kind == 0 ? (double)__ldg((const float *)a.field + id)
+                                               : (double)__ldg((const uint8_t *)a.field + id);
+            double v = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(x, -a.x_min), a.x_range), a.new_range), a.lower);
+            v = __dadd_rn(v, a.add);
+            if (a.quantize) v = (double)(uint16_t)(long long)v;
+            c[j] = v;
+        }
+        const double sd = __dadd_rn(__dadd_rn(d0, d1), d2);
+        const double w0 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d0, 0.00001), sd)), w1 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d1, 0.00001), sd)),
+                     w2 = __ddiv_rn(1.0, __ddiv_rn(__dadd_rn(d2, 0.00001), sd));
+        const double t = __dadd_rn(__dadd_rn(w0, w1), w2);
+        const double v = __dadd_rn(__dadd_rn(__dmul_rn(c[0], __ddiv_rn(w0, t)), __dmul_rn(c[1], __ddiv_rn(w1, t))),
+                                   __dmul_rn(c[2], __ddiv_rn(w2, t)));
+        const int32_t px = (int32_t)v;
+        if (a.out_bits == 8) ((uint8_t *)a.out)[i] = (uint8_t)px; else ((uint16_t *)a.out)[i] = (uint16_t)px;
+    }
+}
+
+NXB_API int nxb_idw_map(const double *dists, const int64_t *ids, const void *field, int field_kind, int64_t n,
+                        double x_min, double x_max, double lower, double upper, double add, int quantize_u16,
+                        int out_bits, void *out, void *stream)
+{
+    NXB_ARG(n >= 0 && (field_kind == 0 || field_kind == 1) && (out_bits == 8 || out_bits == 16));
+    if (n == 0) return NXB_OK;
+    NXB_ARG(dists && ids && field && out);
+    IdwMapArgs a;
+    a.dists = dists; a.ids = (const long long *)ids; a.field = field; a.field_kind = field_kind;
+    a.x_min = x_min; a.x_range = x_max - x_min; a.new_range = upper - lower; a.lower = lower; a.add = add;
+    a.quantize = quantize_u16; a.out_bits = out_bits; a.out = out; a.n = n;
+    idw_map_kernel<<<nxb_grid_resident(idw_map_kernel, 256, 0, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
+}
+
 NXB_API int nxb_idw_gray_f64(const double *dists, const int64_t *ids, const double *colors, int64_t n, int32_t *out, void *stream)
 {
     NXB_ARG(n >= 0);

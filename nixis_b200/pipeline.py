@@ -119,3 +119,31 @@ class TerrainPipeline:
             self._plan = rt.ErosionPlan(self.adj)
             self._dist = _edge_lengths(self.mesh, self.adj)
         return Erosion3State(self.mesh, self.adj, heights32, plan=self._plan, dist=self._dist)
+
+    # ---- equirectangular export, everything stays on the device ------------
+    def image_query(self, width, height):
+        """nixis.py:270-283: per-pixel sphere position and its 3 nearest vertices (dists, ids)."""
+        ll = rt.ll_grid(width, height, self.radius)
+        return rt.ico_nearest3(self.k, self.radius, ll)
+
+    def export_maps(self, heights32, ocean=None, width=4096, height=2048, eroded=False, query=None,
+                    min_alt=MIN_ALT, max_alt=MAX_ALT, ocean_percent=OCEAN_PERCENT):
+        """The maps nixis.py puts in `export_list` and sends through build_image_data, as device
+        images: before erosion `ocean` (uint8), `height_absolute`, `height_relative` (uint16)
+        (nixis.py:349, 386-389); after erosion `height` (uint8, nixis.py:417)."""
+        dists, ids = query if query is not None else self.image_query(width, height)
+        lo, hi = (float(v) for v in rt.minmax(heights32).tolist())
+        maps = {}
+        if eroded:
+            maps["height"] = rt.idw_map(dists, ids, heights32, lo, hi, 0.0, 255.0, out_bits=8)
+            return maps
+        if ocean is not None:
+            # bool mask -> rescale(mask.astype(float64), 0, 255) (util.py:395-396): min 0, max 1
+            m_lo, m_hi = float(ocean.min()), float(ocean.max())
+            maps["ocean"] = rt.idw_map(dists, ids, ocean, m_lo, m_hi, 0.0, 255.0, out_bits=8)
+        add = 32768 - find_percent_val(min_alt, max_alt, ocean_percent)
+        maps["height_absolute"] = rt.idw_map(dists, ids, heights32, lo, hi, min_alt, max_alt, add=add,
+                                             quantize_u16=True, out_bits=16)
+        maps["height_relative"] = rt.idw_map(dists, ids, heights32, lo, hi, 0.0, 65535.0,
+                                             quantize_u16=True, out_bits=16)
+        return maps

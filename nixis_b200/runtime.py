@@ -335,6 +335,18 @@ def idw_gray(dists, ids, colors64):
     return out
 
 
+def idw_map(dists, ids, field, x_min, x_max, lower, upper, add=0.0, quantize_u16=False, out_bits=8):
+    """One export map (nixis.py:349,386-389,417 -> util.py:393-429) from a device-resident field
+    (float32 heights or uint8 mask): rescale + optional uint16 truncation + 3-vertex blend, fused."""
+    assert field.dtype in (torch.float32, torch.uint8) and field.is_contiguous()
+    n = dists.numel() // 3
+    out = torch.empty(dists.shape[:-1], dtype=torch.uint8 if out_bits == 8 else torch.uint16, device=dists.device)
+    _lib.call("nxb_idw_map", _ptr(dists), _ptr(ids), _ptr(field), 0 if field.dtype == torch.float32 else 1, n,
+              C.c_double(x_min), C.c_double(x_max), C.c_double(lower), C.c_double(upper), C.c_double(add),
+              int(bool(quantize_u16)), int(out_bits), _ptr(out), _stream())
+    return out
+
+
 def to_f64(x32):
     out = torch.empty(x32.shape, dtype=torch.float64, device=x32.device)
     _lib.call("nxb_f32_to_f64", _ptr(x32), x32.numel(), _ptr(out), _stream())

@@ -98,3 +98,49 @@ def test_export_config1_4096x2048_d1000_properties(nx):
     v = ((h.to(torch.float64) + 4000.0) * (65535.0 / 12850.0))[ids]
     assert bool((img.to(torch.float64) <= v.max(dim=-1).values + 1e-6).all())
     assert bool((img.to(torch.float64) >= v.min(dim=-1).values.floor() - 1).all())
+
+
+def test_device_export_maps_match_dropin_chain(nx):
+    """the fused device-resident maps (TerrainPipeline.export_maps) equal what the
+    drop-in chain of nixis.py:349,386-389 + build_image_data produces from the same FP32 heights --
+    exactly for the uint16 maps when fed identical per-vertex values, and within 1 level of the
+    float64 numpy chain (FP32 heights feeding int())."""
+    util, rt, torch = nx
+    from nixis_b200.pipeline import TerrainPipeline, find_percent_val
+    k, W, H = 64, 512, 256
+    pipe = TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh(with_adjacency=False)
+    h, ocean, _ = pipe.heights()
+    q = pipe.image_query(W, H)
+    maps = pipe.export_maps(h, ocean, W, H, query=q)
+    assert maps["height_absolute"].dtype == torch.uint16 and maps["ocean"].dtype == torch.uint8
+    dists, nbrs = q[0].cpu().numpy(), q[1].cpu().numpy()
+    h64 = h.cpu().numpy().astype(np.float64)
+
+    def np_rescale(x, lo, hi):                      # util.py:143
+        return ((x - x.min()) / (x.max() - x.min())) * (hi - lo) + lo
+
+    def np_blend(colors):                           # util.py:343-367
+        c = colors.astype(np.float64)[nbrs]
+        sd = dists[..., 0] + dists[..., 1] + dists[..., 2]
+        ws = 1 / ((dists + 0.00001) / sd[..., None])
+        t = ws[..., 0] + ws[..., 1] + ws[..., 2]
+        iw = ws / t[..., None]
+        return (c[..., 0] * iw[..., 0] + c[..., 1] * iw[..., 1] + c[..., 2] * iw[..., 2]).astype(np.int64)
+
+    absolute = (np_rescale(h64, -4000, 8850) + (32768 - find_percent_val(-4000, 8850, 55.0))).astype('uint16')
+    relative = np_rescale(h64, 0, 65535).astype('uint16')
+    assert np.array_equal(maps["height_absolute"].cpu().numpy(), np_blend(absolute).astype('uint16'))
+    assert np.array_equal(maps["height_relative"].cpu().numpy(), np_blend(relative).astype('uint16'))
+    mask = ocean.cpu().numpy().astype(bool)
+    assert np.array_equal(maps["ocean"].cpu().numpy(), np_blend(np_rescale(mask.astype(np.float64), 0, 255)).astype('uint8'))
+    # the same maps through the drop-in functions (host numpy in / out)
+    util.cfg.IMG_QUERY_DATA = (dists, nbrs)
+    res = util.build_image_data({"ocean": [mask, 'gray'], "height_absolute": [absolute, 'gray'],
+                                 "height_relative": [relative, 'gray']})
+    for key in ("ocean", "height_absolute", "height_relative"):
+        assert res[key].dtype == maps[key].cpu().numpy().dtype
+        assert np.abs(res[key].astype(int) - maps[key].cpu().numpy().astype(int)).max() <= (1 if key == "ocean" else 0), key
+    # after erosion: a single uint8 `height` map (nixis.py:417)
+    e = pipe.export_maps(h, None, W, H, eroded=True, query=q)["height"]
+    assert np.array_equal(e.cpu().numpy(), np_blend(np_rescale(h64, 0, 255)).astype('uint8'))

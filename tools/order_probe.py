@@ -1,0 +1,44 @@
+"""Single-GPU probe: cost of processing tiles out of index order in erode3_plan_kernel."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from nixis_b200 import runtime as rt, _lib
+from nixis_b200.pipeline import TerrainPipeline
+k = int(sys.argv[1]) if len(sys.argv) > 1 else 2500
+pipe = TerrainPipeline(k, seed=12345, n_octaves=8)
+pipe.build_mesh()
+h, _, _ = pipe.heights()
+st = pipe.erosion_state(h)
+tp, n_tiles = st.plan, st.plan.n_tiles
+ticket = torch.zeros(4 + 128, dtype=torch.int32, device="cuda")
+def run(order, n=50):
+    src, dst = st.cur, st.nxt
+    def one():
+        nonlocal src, dst
+        _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st.dist),
+                  rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
+                  tp.n_own, C.c_float(0.0), None, None, 0, None, None, None, None, None, 0,
+                  C.c_uint32(0), C.c_uint32(0), 0, rt._ptr(ticket), None if order is None else rt._ptr(order), rt._stream())
+        src, dst = dst, src
+    for _ in range(5): one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): one()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+ident = torch.arange(n_tiles, dtype=torch.int32, device="cuda")
+print(f"k={k} tiles={n_tiles}")
+print("null order        :", round(run(None), 1), "us")
+print("identity order    :", round(run(ident), 1), "us")
+mask = (torch.arange(n_tiles, device="cuda") % 5 == 0)
+o20 = torch.argsort(mask.to(torch.int8), stable=True).to(torch.int32)
+print("every 5th tile last:", round(run(o20), 1), "us")
+blk = ((torch.arange(n_tiles, device="cuda") // 64) % 5 == 0)
+o20b = torch.argsort(blk.to(torch.int8), stable=True).to(torch.int32)
+print("every 5th 64-block last:", round(run(o20b), 1), "us")
+rev = torch.arange(n_tiles - 1, -1, -1, dtype=torch.int32, device="cuda")
+print("reversed          :", round(run(rev), 1), "us")
+perm = torch.randperm(n_tiles, device="cuda").to(torch.int32)
+print("random permutation:", round(run(perm), 1), "us")
