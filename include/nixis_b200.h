@@ -116,6 +116,26 @@ int nxb_idw_map(const double *dists, const int64_t *ids, const void *field, int 
                 double x_min, double x_max, double lower, double upper, double add, int quantize_u16,
                 int out_bits, void *out, void *stream);
 
+/* ---- per-vertex climate kernels ---------------------------------------------------
+ * verts: device float64 [n][3] (the reference's `points`, already scaled by radius).  Every driver
+ * of the reference (360 rotations, 360 days) is ONE pass over the vertices. */
+/* climate.py:345-372 assign_surface_temp (the altitude term is multiplied by the literal 0 there) */
+int nxb_climate_surface_temp_f32(const double *verts, int64_t n, double radius, double tilt, float *out, void *stream);
+/* climate.py:415-448 sample_insolation, repeated for rot_deg[0..n_rot) (HOST, degrees) the way
+ * brute_daily_insolation (:450-490) and calc_insolation_slice (:503-536) drive it, for each of
+ * tilt_deg[0..n_tilt) (HOST, degrees): arr float32 [n_tilt][n] += ..., float32 rounding per rotation.
+ * tilt_scratch: device double[2*n_tilt].  n_rot, n_tilt <= 360. */
+int nxb_climate_insolation_f32(const double *verts, int64_t n, double radius, const double *rot_deg, int n_rot,
+                               const double *tilt_deg, int n_tilt, double *tilt_scratch, float *arr, void *stream);
+/* the 181 lookup vertices of calc_insolation_slice (climate.py:507-515, util.py:80-88), HOST output */
+int nxb_climate_slice_verts(double radius, double *verts_host);
+/* climate.py:193-201 calculate_seasonal_tilt (host) */
+double nxb_climate_seasonal_tilt(double axial_tilt, double degrees);
+/* climate.py:551-577 interpolate_insolation against n_tab tables float32 [n_tab][181]; n_tab > 1 sums
+ * the float32 daily values in table order (calc_yearly_insolation, :579-597) */
+int nxb_climate_interpolate_f32(const double *verts, int64_t n, double radius, const float *tables, int n_tab,
+                                float *out, void *stream);
+
 /* ---- util.py: adjacency -------------------------------------------------- */
 /* util.py:591-613 build_adjacency.  cells int32[T][3]; adj int32[V][6], -1 padded.
  * workspace: device scratch of nxb_adj_build_workspace(V) bytes.  Deterministic

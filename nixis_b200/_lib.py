@@ -38,6 +38,11 @@ SIGNATURES = {
     "nxb_ico_nearest3_f64": (_i, [_i, _d, _p, _i64, _p, _p, _p]),
     "nxb_idw_gray_f64": (_i, [_p, _p, _p, _i64, _p, _p]),
     "nxb_idw_map": (_i, [_p, _p, _p, _i, _i64, _d, _d, _d, _d, _d, _i, _i, _p, _p]),
+    "nxb_climate_surface_temp_f32": (_i, [_p, _i64, _d, _d, _p, _p]),
+    "nxb_climate_insolation_f32": (_i, [_p, _i64, _d, _p, _i, _p, _i, _p, _p, _p]),
+    "nxb_climate_slice_verts": (_i, [_d, _p]),
+    "nxb_climate_seasonal_tilt": (_d, [_d, _d]),
+    "nxb_climate_interpolate_f32": (_i, [_p, _i64, _d, _p, _i, _p, _p]),
     "nxb_adj_build_workspace": (_i64, [_i64]),
     "nxb_adj_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_adj_sort": (_i, [_p, _p, _i64, _p]),
@@ -101,7 +106,7 @@ def check(rc, what=""):
 
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"nxb_adj_build": 2, "nxb_ffma_peak": 5, "nxb_init_perm": 0, "nxb_tables_create": 0,
-                    "nxb_tables_destroy": 0}
+                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0}
 launch_count = 0
 
 

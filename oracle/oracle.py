@@ -20,11 +20,12 @@ _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
     """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
-    srcs = [os.path.join(_HERE, s) for s in ("nixis_oracle.c", "nixis_oracle4.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("nixis_oracle.c", "nixis_oracle4.c", "nixis_oracle_climate.c")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
@@ -68,6 +69,15 @@ def lib():
         L.nxo_erosion_iteration3.argtypes = [C.c_int64, _f64p, _i32p, _f64p, _f64p, _f64p]
         L.nxo_erode_terrain3.argtypes = [C.c_int64, _f64p, _i32p, _f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.nxo_num_threads.restype = C.c_int
+        if hasattr(L, "nxo_sample_insolation"):
+            L.nxo_seasonal_tilt.restype = C.c_double
+            L.nxo_seasonal_tilt.argtypes = [C.c_double, C.c_double]
+            L.nxo_assign_surface_temp.argtypes = [C.c_int64, _f64p, _f64p, C.c_double, C.c_double, _f32p]
+            L.nxo_sample_insolation.argtypes = [C.c_int64, _f32p, _f64p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+            L.nxo_insolation_slice.argtypes = [C.c_double, C.c_double, _f32p]
+            L.nxo_interpolate_insolation.argtypes = [C.c_int64, _f64p, _f32p, _f32p, C.c_double]
+            L.nxo_daily_insolation.argtypes = [C.c_int64, _f64p, C.c_double, C.c_double, _f32p]
+            L.nxo_yearly_insolation.argtypes = [C.c_int64, _f64p, C.c_double, C.c_double, _f32p]
         _lib = L
     return _lib
 
@@ -234,3 +244,60 @@ def height_assembly(height, min_alt=-4000, max_alt=8850, ocean_percent=55.0):
 
 def num_threads():
     return lib().nxo_num_threads()
+
+
+# ---- climate.py -------------------------------------------
+def calculate_seasonal_tilt(axial_tilt, degrees):
+    return lib().nxo_seasonal_tilt(float(axial_tilt), float(degrees))
+
+
+def assign_surface_temp(verts, altitudes, radius, tilt):
+    v = _f64(verts)
+    out = np.zeros(len(v), dtype=np.float32)
+    lib().nxo_assign_surface_temp(len(v), v, _f64(altitudes), float(radius), float(tilt), out)
+    return out
+
+
+def sample_insolation(arr, verts, radius, rotation, tilt):
+    """In place on the float32 array `arr` (climate.py:415-448)."""
+    v = _f64(verts)
+    assert arr.dtype == np.float32 and arr.flags.c_contiguous
+    lib().nxo_sample_insolation(len(v), arr, v, float(radius), float(rotation), 0.0, 1, float(tilt))
+
+
+def brute_daily_insolation(verts, altitudes, radius, tilt, snapshot=False):
+    v = _f64(verts)
+    out = np.zeros(len(v), dtype=np.float32)
+    lib().nxo_sample_insolation(len(v), out, v, float(radius), -180.0, 360.0 / 360, 360, float(tilt))
+    return out
+
+
+def calc_instant_insolation(verts, altitudes, radius, rotation, tilt):
+    out = np.zeros(len(verts), dtype=np.float32)
+    sample_insolation(out, verts, radius, rotation, tilt)
+    return out
+
+
+def calc_insolation_slice(radius, tilt):
+    out = np.zeros(181, dtype=np.float32)
+    lib().nxo_insolation_slice(float(radius), float(tilt), out)
+    return out
+
+
+def interpolate_insolation(verts, lookup_table, insolation, radius):
+    v = _f64(verts)
+    lib().nxo_interpolate_insolation(len(v), v, np.ascontiguousarray(lookup_table, dtype=np.float32), insolation, float(radius))
+
+
+def calc_daily_insolation(verts, altitudes, radius, tilt):
+    v = _f64(verts)
+    out = np.zeros(len(v), dtype=np.float32)
+    lib().nxo_daily_insolation(len(v), v, float(radius), float(tilt), out)
+    return out
+
+
+def calc_yearly_insolation(points, height, radius, axial_tilt, snapshot=False):
+    v = _f64(points)
+    out = np.zeros(len(v), dtype=np.float32)
+    lib().nxo_yearly_insolation(len(v), v, float(radius), float(axial_tilt), out)
+    return out

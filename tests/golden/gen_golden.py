@@ -235,6 +235,34 @@ def gen_export():
     save("export.npz", **out)
 
 
+def gen_climate():
+    """the per-vertex climate kernels of climate.py:345-597, reference code."""
+    os.chdir(REF)
+    import climate
+    os.chdir(_cwd)
+    out = {}
+    rng = np.random.default_rng(777)
+    for k, R in ((8, EARTH_R), (12, 1.0)):
+        pts, _ = icosphere.icosa_sphere(k)
+        P = np.ascontiguousarray(pts * R)
+        h = rng.uniform(-4000.0, 8850.0, len(P))
+        t = f"k{k}"
+        out[f"{t}_R"] = np.array([R])
+        out[f"{t}_height"] = h
+        tilts = [climate.calculate_seasonal_tilt(23.44, 36), 0.0, -23.44, 80.0]
+        out[f"{t}_tilts"] = np.array(tilts)
+        for i, tilt in enumerate(tilts):
+            out[f"{t}_temp_{i}"] = climate.assign_surface_temp(P, h, R, tilt)
+            out[f"{t}_slice_{i}"] = climate.calc_insolation_slice(R, tilt)
+            out[f"{t}_daily_{i}"] = climate.calc_daily_insolation(P, h, R, tilt)
+            for j, rot in enumerate((0, 37.5, -180.0)):
+                out[f"{t}_instant_{i}_{j}"] = climate.calc_instant_insolation(P, h, R, rot, tilt)
+        out[f"{t}_brute_0"] = climate.brute_daily_insolation(P, h, R, tilts[0])
+        out[f"{t}_yearly"] = climate.calc_yearly_insolation(P, h, R, 23.44)
+    out["seasonal_tilt"] = np.array([climate.calculate_seasonal_tilt(23.44, d) for d in range(360)])
+    save("climate.npz", **out)
+
+
 def main():
     print("reference:", REF)
     gen_init()
@@ -244,6 +272,7 @@ def main():
     gen_assembly()
     gen_erosion()
     gen_export()
+    gen_climate()
     # provenance
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         import numba
@@ -253,7 +282,7 @@ def main():
             if fn.endswith(".npz"):
                 sha = hashlib.sha1(open(os.path.join(HERE, fn), "rb").read()).hexdigest()[:16]
                 f.write(f"{fn} sha1={sha}\n")
-        for src in ("opensimplex.py", "terrain.py", "util.py", "erosion.py"):
+        for src in ("opensimplex.py", "terrain.py", "util.py", "erosion.py", "climate.py"):
             sha = hashlib.sha1(open(os.path.join(REF, src), "rb").read()).hexdigest()[:16]
             f.write(f"reference/{src} sha1={sha}\n")
 
