@@ -10,6 +10,7 @@ outside the path and not provided here.
 numpy in -> numpy out (float64 / int32, like the reference); `DeviceMesh` and CUDA tensors
 in -> CUDA tensors out (the resident path bench.py and the multi-GPU driver use).
 """
+import os
 import time
 
 import numpy as np
@@ -272,3 +273,114 @@ def build_image_data(colors=None, width=None, height=None):
         else:
             result[key] = pixels.astype(array.dtype)
     return result
+
+
+# ---------------------------------------------------------------------------------------------
+# File I/O and scalar helpers: host-side, same names as util.py:59-98, 430-553.
+# Nothing here touches the GPU; options default to the reference's options.json values.
+DEFAULT_OPTIONS = {"img_format": "png", "mesh_format": "obj", "point_format": "ply", "settings_format": "json"}
+
+
+def xyz2latlon(x, y, z, r):
+    """util.py:59-75."""
+    lat = np.degrees(np.arcsin(min(max((z / r), -1), 1)))
+    lon = np.degrees(np.arctan2(y, x))
+    return (lat, lon)
+
+
+def latlon2xyz(lat, lon, r):
+    """util.py:79-88."""
+    x = r * np.cos(lat * (np.pi / 180)) * np.cos(lon * (np.pi / 180))
+    y = r * np.cos(lat * (np.pi / 180)) * np.sin(lon * (np.pi / 180))
+    z = r * np.sin(lat * (np.pi / 180))
+    return (x, y, z)
+
+
+def kelvin_to_c(k):
+    return k - 273.15
+
+
+def c_to_kelvin(c):
+    return c + 273.15
+
+
+def load_settings(path):
+    """util.py:531-541: JSON file -> dict; a missing file prints and exits like the reference."""
+    import json
+    import sys
+    if os.path.exists(path):
+        with open(path, "rt") as f:
+            return json.loads(f.read())
+    print("Path does not exist:", path)
+    sys.exit(0)
+
+
+def save_settings(data, path, name, fmt=None):
+    """util.py:524-529."""
+    import json
+    with open(os.path.join(path, f"{name}.{fmt}"), "w") as f:
+        json.dump(data, f, indent=4)
+
+
+def _options():
+    return load_settings("options.json") if os.path.exists("options.json") else dict(DEFAULT_OPTIONS)
+
+
+def save_image(data, path, name):
+    """util.py:430-445: one image file per key, `name_key.fmt` (uint8 -> 8-bit, uint16 -> 16-bit gray)."""
+    from PIL import Image
+    fmt = _options()["img_format"]
+    for key, array in data.items():
+        if isinstance(array, torch.Tensor):
+            array = rt._to_host(array)
+        Image.fromarray(array).save(os.path.join(path, f"{name}_{key}.{fmt}"))
+
+
+def image_to_array(image_file):
+    """util.py:447-470: image -> float64 heights in [0, 1)."""
+    import sys
+    from PIL import Image
+    img = Image.open(image_file)
+    if img.mode == "L":
+        return np.float64(np.asarray(img)) / 256
+    if img.mode in ("I", "I;16"):
+        return np.asarray(img) / 65536
+    if img.mode in ("RGB", "RGBA"):
+        return np.float64(np.asarray(img.convert("L"))) / 256
+    print("ERROR. Unsupported image format.")
+    sys.exit(-1)
+
+
+def save_mesh(verts, tris, path, name, confirm=True):
+    """util.py:472-497.  The reference hands the arrays to meshio (absent here); the configured
+    format is Wavefront OBJ, written directly: `v x y z` per vertex, `f a b c` (1-based) per triangle."""
+    if len(tris) > 3000000 and confirm:
+        print("\n" + f"ATTENTION. This mesh has {len(tris):,} triangles. "
+              "Your 3D modeling software may not be able to open/edit it." + "\n")
+        if input("Continue anyway? Y/N: ").lower() not in ('y', 'yes'):
+            print("A smaller division setting will reduce the number of tris.")
+            return
+    fmt = _options()["mesh_format"]
+    if fmt != "obj":
+        raise NotImplementedError(f"mesh_format {fmt!r}: only obj is written without meshio")
+    print("Saving mesh to disk...")
+    t0 = time.perf_counter()
+    verts = np.asarray(verts.cpu() if isinstance(verts, torch.Tensor) else verts, dtype=np.float64)[:, :3]
+    tris = np.asarray(tris.cpu() if isinstance(tris, torch.Tensor) else tris).astype(np.int64) + 1
+    with open(os.path.join(path, f"{name}.{fmt}"), "w") as f:
+        np.savetxt(f, verts, fmt="v %.17g %.17g %.17g")
+        np.savetxt(f, tris, fmt="f %d %d %d")
+    print(f"Mesh saved in {time.perf_counter() - t0 :.5f} sec")
+
+
+def save_point_cloud(verts, path, name):
+    """util.py:499-522."""
+    print("Not implemented yet.")
+
+
+def save_log(path, name, fmt=None):
+    print("Not implemented yet.")
+
+
+def export_planet(data, path, name):
+    print("Not implemented yet.")
