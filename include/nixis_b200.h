@@ -212,6 +212,8 @@ int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, cons
                                   const void *flags, const int32_t *wait_rank, int n_wait,
                                   uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
                                   void *ticket, const int32_t *tile_order /* nullable: processing order */,
+                                  int64_t n_early /* > 0: the first n_early tiles of tile_order are the boundary
+                                  set (send or read halo); flags go up when they are done, not at grid end */,
                                   void *stream);
 /* Reference-exact mode of the sweep: float64 positions / state, no FMA, the reference's operation and
  * neighbour order -> bit-identical to erosion_iteration3 (erosion.py:197-279) preceded by
@@ -235,6 +237,9 @@ int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send_idx, in
 /* Stream-ordered wait until flags[src_ranks[i]] >= target for all i (flags: this rank's uint32 array,
  * written by the peers' nxb_halo_put_f32; src_ranks: device int32[npeers]). */
 int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, void *stream);
+/* the same wait as stream memory operations (cuStreamWaitValue32, one per flag): no kernel, no SM.
+ * src_ranks_host: HOST int32[npeers]. */
+int nxb_halo_wait_stream(const void *flags, const int32_t *src_ranks_host, int npeers, uint32_t target, void *stream);
 
 /* gather / scatter of halo values for the multi-GPU exchange: dst[i] = src[idx[i]] and
  * dst[idx[i]] = src[i] */

@@ -57,11 +57,12 @@ SIGNATURES = {
     "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
     "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
-                                           _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _p]),
+                                           _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _i64, _p]),
     "nxb_erode3_step_f64": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _d, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "nxb_halo_put_f32": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
     "nxb_halo_wait": (_i, [_p, _p, _i, C.c_uint32, _p]),
+    "nxb_halo_wait_stream": (_i, [_p, _p, _i, C.c_uint32, _p]),
     "nxb_gather_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_scatter_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_f32_to_f64": (_i, [_p, _i64, _p, _p]),
@@ -106,7 +107,7 @@ def check(rc, what=""):
 
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"nxb_adj_build": 2, "nxb_ffma_peak": 5, "nxb_init_perm": 0, "nxb_tables_create": 0,
-                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0}
+                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0, "nxb_halo_wait_stream": 0}
 launch_count = 0
 
 

@@ -71,6 +71,12 @@ struct EroComm {
     // read halo slots LAST, so by the time a CTA reaches them the peers' flags are already up and
     // the wait hides behind interior work.
     const int32_t *tile_order;
+    // > 0: the first n_early tiles of the processing order are the boundary set (every tile that
+    // sends or reads halo slots).  The flags are raised as soon as those tiles are done -- their
+    // boundary values are in the peers' memory and this rank no longer reads its halo slots of this
+    // sweep -- not at the end of the grid, so the flag latency, the peers' launch gap and this rank's
+    // tail hide behind the interior tiles.
+    int n_early;
 };
 
 struct EroPlanArgs {
@@ -133,7 +139,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
         dbg_c0 = clock64();
-        a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 0] = (unsigned)dbg_t0;
+        a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 0] = (unsigned)dbg_t0;
     }
 #endif
     if (warp == 0) {
@@ -202,7 +208,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                         if (spun) { atomicAdd(a.comm.ticket + 1, 1u); atomicMax(a.comm.ticket + 2, (unsigned)(t1 - t0)); }
                         atomicMax(a.comm.ticket + 3, (unsigned)it);
-                        if (blockIdx.x == 0 && lane == 0) a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 1] = (unsigned)t1;
+                        if (blockIdx.x == 0 && lane == 0) a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 1] = (unsigned)t1;
 #endif
                     }
                     __threadfence_system();
@@ -282,20 +288,52 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     cta_sent = true;
                 }
             }
+            const int64_t slot = (int64_t)blockIdx.x + it * gridDim.x;
+            if (slot < a.comm.n_early && slot + gridDim.x >= a.comm.n_early) {
+                // this CTA's LAST boundary tile is done: all 8 consumer warps have read their inputs
+                // and stored to the peers.  One system fence per CTA (a fence per tile costs
+                // microseconds each while NVLink stores are in flight), then check in.
+                asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
+                if (c == 0) {
+                    __threadfence_system();         // cumulative over the CTA's peer stores (barrier above)
+                    const unsigned n_cta = a.comm.n_early < (int)gridDim.x ? (unsigned)a.comm.n_early : gridDim.x;
+                    if (atomicAdd(a.comm.ticket, 1u) == n_cta - 1u) {
+                        *a.comm.ticket = 0;
+                        __threadfence_system();
+                        for (int p = 0; p < a.comm.n_send_peers; ++p) {
+                            volatile uint32_t *f = a.comm.peer_flag[p];
+                            *f = a.comm.flag_value;
+                        }
+                        __threadfence_system();
+#ifdef NXB_ERO_DEBUG_WAIT
+                        { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                          a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
+#endif
+                    }
+                }
+            }
         }
     }
 #ifdef NXB_ERO_DEBUG_WAIT
+    if (a.comm.ticket && (tid == 0 || tid == 32)) {           // when did this CTA's producer / consumers run dry
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(a.comm.ticket + 4 + 8 * (a.comm.flag_value % 32) + (tid == 0 ? 4 : 5), (unsigned)t);
+    }
     if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {       // SM clock (MHz) seen by CTA 0 over its lifetime
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         long long c1 = clock64();
-        a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 3] = (unsigned)((c1 - dbg_c0) * 1000 / (long long)(t1 - dbg_t0 + 1));
+        a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 3] = (unsigned)((c1 - dbg_c0) * 1000 / (long long)(t1 - dbg_t0 + 1));
     }
 #endif
-    if (a.comm.n_send_peers > 0) {
+    if (a.comm.n_send_peers > 0 && a.comm.n_early == 0) {
         // every peer store of this CTA is visible system-wide before the CTA checks in; the last
         // CTA of the grid then raises this rank's flag in every peer
         if (cta_sent) __threadfence_system();
         __syncthreads();
+#ifdef NXB_ERO_DEBUG_WAIT
+        if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                        atomicMax(a.comm.ticket + 4 + 8 * (a.comm.flag_value % 32) + 6, (unsigned)t); }
+#endif
         if (tid == 0) s_last = (atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1);
         __syncthreads();
         if (s_last) {
@@ -308,7 +346,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             if (tid == 0) *a.comm.ticket = 0;
 #ifdef NXB_ERO_DEBUG_WAIT
             if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                            a.comm.ticket[4 + 4 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
+                            a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
 #endif
         }
     }
@@ -473,8 +511,9 @@ NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *a
                                           void *const *peer_h, void *const *peer_w, void *const *peer_flag,
                                           const void *flags, const int32_t *wait_rank, int n_wait,
                                           uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
-                                          void *ticket, const int32_t *tile_order, void *stream)
+                                          void *ticket, const int32_t *tile_order, int64_t n_early, void *stream)
 {
+    NXB_ARG(n_early >= 0 && n_early < (1ll << 31) && (n_early == 0 || (tile_order && n_send_peers > 0)));
     NXB_ARG(n_send_peers >= 0 && n_send_peers <= ERO_MAX_PEERS && n_wait >= 0 && n_wait <= ERO_MAX_PEERS);
     NXB_ARG(n_send_peers == 0 || (send_ptr && send_entries && peer_h && peer_w && peer_flag && ticket));
     NXB_ARG(n_wait == 0 || (flags && wait_rank));
@@ -493,6 +532,7 @@ NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *a
     comm.n_wait = n_wait;
     comm.wait_target = wait_target; comm.flag_value = flag_value; comm.halo_begin = halo_begin;
     comm.tile_order = tile_order;
+    comm.n_early = (int)n_early;
     return erode3_plan_launch(plan_mem, adj, dist, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
 }
 

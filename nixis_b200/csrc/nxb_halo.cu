@@ -111,3 +111,39 @@ NXB_API int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeer
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
+
+// The same wait without a kernel: one stream memory operation per source flag
+// (cuStreamWaitValue32, GEQ = wrap-safe "(int32)(*flag - target) >= 0").  The stream stalls in
+// the front end, no SM is occupied and no launch / drain sits between two sweeps.  src_ranks: HOST.
+// The driver entry point is resolved at run time (no link dependency on libcuda).
+#include <cuda.h>
+typedef CUresult (*nxb_wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static nxb_wait32_fn nxb_wait32()
+{
+    static nxb_wait32_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (nxb_wait32_fn)p;
+    }
+    return fn;
+}
+
+NXB_API int nxb_halo_wait_stream(const void *flags, const int32_t *src_ranks_host, int npeers, uint32_t target, void *stream)
+{
+    NXB_ARG(npeers >= 0 && npeers <= 32);
+    if (npeers == 0) return NXB_OK;
+    NXB_ARG(flags && src_ranks_host);
+    nxb_wait32_fn fn = nxb_wait32();
+    if (!fn) { nxb_set_error("cuStreamWaitValue32 is not available from this driver"); return NXB_ERR_CUDA; }
+    for (int i = 0; i < npeers; ++i) {
+        const CUdeviceptr a = (CUdeviceptr)((const uint32_t *)flags + src_ranks_host[i]);
+        const CUresult r = fn((CUstream)stream, a, target, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) { nxb_set_error("cuStreamWaitValue32 -> CUresult %d", (int)r); return NXB_ERR_CUDA; }
+    }
+    return NXB_OK;
+}

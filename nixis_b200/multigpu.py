@@ -74,7 +74,7 @@ class ShardedErosion:
         self.hw = [(self._buf[0:c], self._buf[c:2 * c]), (self._buf[2 * c:3 * c], self._buf[3 * c:4 * c])]
         self.sed = [torch.zeros(c, dtype=torch.float32, device=dev), torch.zeros(c, dtype=torch.float32, device=dev)]
         self.flags = self._buf[4 * c:4 * c + 64].view(torch.int32)      # one uint32 per source rank
-        self.ticket = torch.zeros(4 + 128, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(4 + 256, dtype=torch.int32, device=dev)
         self.cur = 0
         self._pending = False               # a publish has been issued whose incoming flags were not awaited yet
         # concatenated send list, peer after peer
@@ -89,6 +89,9 @@ class ShardedErosion:
         self._src_begin = _i64_array(np.concatenate([[0], np.cumsum(counts)[:-1]]) if counts else [])
         self._dst_off = _i64_array([plan.peer_n_own_pad[p] + plan.send_dst_offset[p] for p in self.send_peers])
         self.recv_ranks = torch.tensor(self.recv_peers if self.recv_peers else [0], dtype=torch.int32, device=dev)
+        self._recv_ranks_host = (C.c_int32 * max(1, len(self.recv_peers)))(*self.recv_peers)
+        # "kernel": one-warp spin kernel; "stream": cuStreamWaitValue32 memory operations (no launch)
+        self.wait_mode = os.environ.get("NXB_HALO_WAIT", "kernel")
         if self.transport == "fused":
             self._build_send_table()
         if self.world > 1:
@@ -126,6 +129,13 @@ class ShardedErosion:
         needs_halo = ((seg_start >= plan.n_own_pad) & live).any(dim=1) | (irregular != 0)
         self.tile_order = torch.argsort(needs_halo.to(torch.int8), stable=True).to(torch.int32).contiguous()
         self.n_halo_tiles = int(needs_halo.sum().item())
+        # boundary set = tiles that send or read halo slots, FIRST (early flag mode)
+        boundary = needs_halo | (counts > 0)
+        self.boundary_order = torch.argsort((~boundary).to(torch.int8), stable=True).to(torch.int32).contiguous()
+        self.n_boundary_tiles = int(boundary.sum().item())
+        self.fused_mode = os.environ.get("NXB_FUSED_MODE", "inkernel" if os.environ.get("NXB_FUSED_INKERNEL_WAIT") else "sepwait")
+        if self.fused_mode == "early" and (self.n_boundary_tiles == 0 or not self.send_peers):
+            self.fused_mode = "sepwait"
 
     # ------------------------------------------------------------------------------------
     def load(self, heights_own):
@@ -162,8 +172,12 @@ class ShardedErosion:
     def _await(self):
         self._pending = False
         if self.world > 1 and self.transport in ("nvlink", "fused") and self.recv_peers:
-            _lib.call("nxb_halo_wait", rt._ptr(self.flags), rt._ptr(self.recv_ranks), len(self.recv_peers),
-                      C.c_uint32(self.sweeps + 1), rt._stream())
+            if self.wait_mode == "stream":
+                _lib.call("nxb_halo_wait_stream", rt._ptr(self.flags), self._recv_ranks_host, len(self.recv_peers),
+                          C.c_uint32(self.sweeps + 1), rt._stream())
+            else:
+                _lib.call("nxb_halo_wait", rt._ptr(self.flags), rt._ptr(self.recv_ranks), len(self.recv_peers),
+                          C.c_uint32(self.sweeps + 1), rt._stream())
 
     def _peer_ptrs(self, which):
         c = self.cap
@@ -184,8 +198,13 @@ class ShardedErosion:
             # NXB_FUSED_INKERNEL_WAIT=1) works and is bit-identical, but measured bistable on 2 GPUs --
             # the ranks either stay in lockstep (333 us/sweep) or fall into a wait/compute alternation
             # (635 us/sweep); see profiles/r01_fused_wait_timeline.txt.
-            n_wait, wait_target, order = 0, 0, None
-            if os.environ.get("NXB_FUSED_INKERNEL_WAIT"):
+            n_wait, wait_target, order, n_early = 0, 0, None, 0
+            if self.fused_mode == "early":
+                # boundary tiles first, flags raised as soon as they are done, wait inside the kernel
+                # (the peers' flags of the previous sweep went up a whole interior phase ago)
+                n_wait, wait_target = len(self.recv_peers), self.sweeps + 1
+                order, n_early = rt._ptr(self.boundary_order), self.n_boundary_tiles
+            elif self.fused_mode == "inkernel":
                 n_wait, wait_target = len(self.recv_peers), self.sweeps + 1
                 order = rt._ptr(self.tile_order) if os.environ.get("NXB_FUSED_TILE_ORDER") else None
             else:
@@ -196,7 +215,7 @@ class ShardedErosion:
                       rt._ptr(self.send_ptr), rt._ptr(self.send_entries), len(self.send_peers), ph, pw, pf,
                       rt._ptr(self.flags), self._wait_rank, n_wait,
                       C.c_uint32(wait_target), C.c_uint32(self.sweeps + 2), self.plan.n_own_pad,
-                      rt._ptr(self.ticket), order, rt._stream())
+                      rt._ptr(self.ticket), order, n_early, rt._stream())
             self._pending = True
             self.cur = 1 - self.cur
             self.sweeps += 1
@@ -242,7 +261,9 @@ class ShardedTerrain:
         self.tables = rt.tables_for(self.perm, self.pgi)
         self.freq, self.amp = rt.octave_schedule(n_octaves, N_INIT_ROUGH, N_INIT_STRENGTH, N_ROUGHNESS, N_PERSISTENCE)
         self.coll = Collective(group, distributed=True)
-        self.ranges = vertex_ranges(self.V, self.world)
+        # the skeleton's tiles are the irregular ones of the sweep planner (~6x a regular tile)
+        self.ranges = vertex_ranges(self.V, self.world, front=12 + 30 * (self.k - 1),
+                                    front_cost=float(os.environ.get("NXB_SKELETON_COST", "6")))
         self.begin, self.end = self.ranges[self.rank]
         self.n_own = self.end - self.begin
         # mesh shard (positions of the own range only)

@@ -29,14 +29,26 @@ def round_up(n, m):
     return (n + m - 1) // m * m
 
 
-def vertex_ranges(n_vertices: int, world: int, align: int = TILE):
-    """Contiguous, tile-aligned, near-equal ranges; the last rank takes the remainder."""
-    per = round_up((n_vertices + world - 1) // world, align)
-    out = []
+def vertex_ranges(n_vertices: int, world: int, align: int = TILE, front: int = 0, front_cost: float = 1.0):
+    """Contiguous, tile-aligned ranges of near-equal COST; the last rank takes the remainder.
+    The first `front` vertices cost `front_cost` each, the rest 1: the mesh skeleton (12 corners + 30
+    edge runs) sits at the front of the index space, its tiles gather their neighbours from global
+    memory instead of staged runs and measure ~6x a regular tile, so rank 0 gets fewer vertices."""
+    front = min(max(int(front), 0), n_vertices)
+    extra = front * (front_cost - 1.0)
+    per_cost = (n_vertices + extra) / world
+
+    def vertex_at(cost):                      # smallest vertex count whose cumulative cost >= cost
+        if cost <= front * front_cost:
+            return cost / front_cost
+        return cost - extra
+
+    out, b = [], 0
     for r in range(world):
-        b = min(r * per, n_vertices)
-        e = min((r + 1) * per, n_vertices)
+        e = n_vertices if r == world - 1 else min(round_up(int(-(-vertex_at((r + 1) * per_cost) // 1)), align), n_vertices)
+        e = max(e, b)
         out.append((b, e))
+        b = e
     return out
 
 

@@ -21,7 +21,8 @@ def gather_own(t, terr):
     dist.all_gather(bufs, pad)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
 
-for transport in ("fused", "nvlink", "p2p"):
+TRANSPORTS = os.environ.get("MGPU_TRANSPORTS", "fused,nvlink,p2p").split(",")
+for transport in TRANSPORTS:
     for k, sweeps in ((64, 25), (200, 10)):
         terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
         h, ocean, lvl = terr.heights()
@@ -49,7 +50,7 @@ for transport in ("fused", "nvlink", "p2p"):
 
 # timings at scale
 k = int(os.environ.get("MGPU_K", "2500"))
-for transport in ("fused", "nvlink", "p2p"):
+for transport in ([] if os.environ.get("MGPU_SKIP_TIMING") else TRANSPORTS):
     terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
     h, _, _ = terr.heights()
     ero = terr.erosion

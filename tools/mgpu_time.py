@@ -36,11 +36,13 @@ for transport in os.environ.get("MGPU_TRANSPORTS", "fused,nvlink").split(","):
     if rank == 0:
         print(f"[{transport}] compute-only us/sweep per rank: {[round(t.item(), 1) for t in allt]} irregular tiles per rank: {[int(t.item()) for t in alli]} of {ero.tile_plan.n_tiles}", flush=True)
     tk = ero.ticket.tolist()
-    rows = sorted([tk[4 + 4 * i: 4 + 4 * i + 4] for i in range(32)], key=lambda r: r[0] & 0xffffffff)
+    rows = sorted([tk[4 + 8 * i: 4 + 8 * i + 8] for i in range(32)], key=lambda r: r[0] & 0xffffffff)
     rows = [[x & 0xffffffff for x in r] for r in rows if r[0]]
     base = rows[0][0] if rows else 0
-    print(f"rank {rank} timeline (us since first): " + " | ".join(f"{(r[0]-base)/1e3:.0f} +{(r[1]-r[0])/1e3:.0f} +{(r[2]-r[0])/1e3:.0f} {r[3]}MHz" for r in rows[:10]), flush=True)
-    print(f"rank {rank} [{transport}] debug ticket words {tk[:4]} halo tiles {getattr(ero, 'n_halo_tiles', None)} of {ero.tile_plan.n_tiles}", flush=True)
+    us = lambda r, i: f"{(r[i] - r[0]) / 1e3:.0f}" if r[i] else "-"
+    print(f"rank {rank} timeline (start us | +producers dry, +consumers dry, +last CTA past fence, +flag raised): " +
+          " | ".join(f"{(r[0]-base)/1e3:.0f}: +{us(r,4)} +{us(r,5)} +{us(r,6)} +{us(r,2)}" for r in rows[:8]), flush=True)
+    print(f"rank {rank} [{transport}] debug ticket words {tk[:4]} halo tiles {getattr(ero, 'n_halo_tiles', None)} boundary tiles {getattr(ero, 'n_boundary_tiles', None)} mode {getattr(ero, 'fused_mode', None)} of {ero.tile_plan.n_tiles}", flush=True)
     del terr, ero
     torch.cuda.empty_cache()
 dist.destroy_process_group()
