@@ -188,10 +188,16 @@ int nxb_mesh_icosa_edge_lengths(int k, const int32_t *adj_rows, int64_t v_begin,
 int64_t nxb_erode_plan_bytes(int64_t n_own);
 int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, void *plan_mem,
                          int32_t *stats_host, void *stream);
+/* One stored length per edge: dist3[v][i] = dist[v][q] of v's i-th larger-numbered neighbour (slot
+ * order), float[round_up(n_own,256)][3].  With it the sweep streams 12 B/vertex of edge lengths
+ * instead of 24 (48 B per vertex-iteration instead of 60); the plan's code bits say which row holds
+ * each slot's length.  Pass dist3 = NULL to the step functions to stream the full table. */
+int64_t nxb_erode_dist3_floats(int64_t n_own);   /* size of the dist3 buffer: the rows plus the tiles' exception rows */
+int nxb_erode_dist3_build(const void *plan_mem, const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream);
 /* erosion.py:197-279 erosion_iteration3 for vertices [0, n_own), FP32 state, ping-pong buffers
  * (reads *_in, writes *_out; no copy-back pass).  `rain` is added to every water value read
  * (erosion.py:182-183 `water += rain_amount` fused).  dist: float[round_up(n_own,256)*6]. */
-int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                              const float *h_in, const float *w_in, const float *s_in,
                              float *h_out, float *w_out, float *s_out,
                              int64_t n_own, float rain, void *stream);
@@ -203,7 +209,7 @@ int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const flo
  * pointers (peers' OUTPUT buffers of this sweep, their flag slot for this rank); flags: this rank's
  * uint32 flag array; wait_rank: host int32[n_wait]; halo_begin: first halo slot; ticket: device
  * uint32 (zero). */
-int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                                   const float *h_in, const float *w_in, const float *s_in,
                                   float *h_out, float *w_out, float *s_out,
                                   int64_t n_own, float rain,

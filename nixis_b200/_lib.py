@@ -55,8 +55,10 @@ SIGNATURES = {
     "nxb_mesh_icosa_edge_lengths": (_i, [_i, _p, _i64, _i64, _d, _p, _p]),
     "nxb_erode_plan_bytes": (_i64, [_i64]),
     "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
-    "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
-    "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
+    "nxb_erode_dist3_floats": (_i64, [_i64]),
+    "nxb_erode_dist3_build": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
+    "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
                                            _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _i64, _p]),
     "nxb_erode3_step_f64": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _d, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
@@ -107,7 +109,7 @@ def check(rc, what=""):
 
 # kernels launched per successful call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {"nxb_adj_build": 2, "nxb_ffma_peak": 5, "nxb_init_perm": 0, "nxb_tables_create": 0,
-                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0, "nxb_halo_wait_stream": 0}
+                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0, "nxb_halo_wait_stream": 0, "nxb_erode_dist3_build": 2}
 launch_count = 0
 
 

@@ -19,16 +19,22 @@
 //     are the tile itself plus <= 6 contiguous index runs (mesh rows above / below, the elements
 //     next to the tile ends).  A producer warp brings the tile's own streams AND those runs of
 //     h / w into shared memory with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an
-//     mbarrier, ERO_STAGES tiles ahead; eight consumer warps then read every neighbour value from
+//     mbarrier, n_stages tiles ahead; eight consumer warps then read every neighbour value from
 //     shared memory through a 16-bit tile-local adjacency.  No global gathers, no L1 dependence.
 //     The halo runs were just streamed by a neighbouring tile, so they come from L2, not HBM.
+//   * ONE LENGTH PER EDGE (dist3, nxb_erosion_plan.cuh) is implemented and bit-identical, but OFF by
+//     default: it cuts the DRAM reads from 3.16 GB to 2.53 GB per sweep at d = 2500 (ncu) and still
+//     runs 715-750 us against 590 us, because at 590 us the consumer warps are already issue-bound
+//     (72 % issue-slot utilisation, ~230 instructions per vertex) and decoding which row holds a
+//     slot's length adds ~60 instructions per vertex.  Enable with NXB_ERO_DIST3=1.
 //   * ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
 //     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
 #include "nxb_common.cuh"
 #include "nxb_erosion_plan.cuh"
 #include <string.h>
+#include <stdlib.h>
 
-#define ERO_STAGES 4
+#define ERO_STAGES_MAX 4          // pipeline depth is a launch parameter (3: 4 CTAs/SM, 4: 3 CTAs/SM)
 #define ERO_CONSUMER_WARPS (ERO_TILE / 32)
 #define ERO_THREADS (ERO_TILE + 32)
 
@@ -36,11 +42,13 @@ struct __align__(128) EroStage {
     float h[ERO_STAGE_ELEMS];           // [own tile | halo segments]
     float w[ERO_STAGE_ELEMS];
     float s[ERO_TILE];
-    float dist[ERO_TILE * 6];
+    float dist[ERO_TILE * 3 + ERO_D3_CAP * 3];   // kind 1: [256][6] full rows; kind 0: dist3 [own 256 | staged halo slots]
     uint16_t adj[ERO_TILE * 6];
+    float exc[ERO_EXC * 6];             // kind 0: full rows of the tile's heavy vertices
     int32_t irregular;
     int32_t tile;
-    int32_t pad[30];
+    int32_t kind;                       // 0: dist holds dist3 rows, 1: full rows
+    int32_t pad[5];
 };
 
 #define ERO_MAX_PEERS 8
@@ -82,7 +90,11 @@ struct EroComm {
 struct EroPlanArgs {
     const EroTileDesc *desc; const uint16_t *adj16;     // plan
     const int32_t *adj;                                 // int32 ELL (irregular tiles only)
-    const float *dist;
+    const float *dist;                                  // full table [.][6]
+    const float *dist3;                                 // one entry per edge [.][3] (null: full table only)
+    const float *exc;                                   // [n_tiles][ERO_EXC][6] rows of heavy vertices
+    int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
+    unsigned wait_ns;                                   // consumers sleep this long between barrier polls (0: spin)
     const float *h_in, *w_in, *s_in;
     float *h_out, *w_out, *s_out;
     int64_t n_own;
@@ -101,10 +113,18 @@ __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         const float wq = wn[q] + rain;
-        // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0
+        // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0.
+        //   dh > 0: sed_amt += sol * wq, wat_amt += wq * d;   dh < 0: the same with a minus sign;
+        //   dh == 0 or NaN: nothing (erosion.py:232-247).
+        // Branch-free: the sign bit of dh is copied onto sol and wq, then two predicated FMAs --
+        // the very FMAs the branchy form contracts to, so results are bit-identical to it.
         const float dh = hn[q] - me;
-        if (dh > 0.0f)      { sed_amt += solubility * wq; wat_amt += wq * d[q]; }
-        else if (dh < 0.0f) { sed_amt -= solubility * wq; wat_amt -= wq * d[q]; }
+        const uint32_t sgn = __float_as_uint(dh) & 0x80000000u;
+        const float ssol = __uint_as_float(__float_as_uint(solubility) | sgn);
+        const float swq = __uint_as_float(__float_as_uint(wq) ^ sgn);
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.f32 p, %2, 0f00000000;\n\t"
+            "@p fma.rn.f32 %0, %3, %4, %0;\n\t@p fma.rn.f32 %1, %5, %6, %1;\n\t}"
+            : "+f"(sed_amt), "+f"(wat_amt) : "f"(dh), "f"(ssol), "f"(wq), "f"(swq), "f"(d[q]));
     }
     hh = me - sed_amt;
     ss = sed_i + sed_amt;
@@ -118,7 +138,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     EroStage *stage = reinterpret_cast<EroStage *>(smem_raw);
-    __shared__ __align__(8) uint64_t full[ERO_STAGES], empty[ERO_STAGES];
+    __shared__ __align__(8) uint64_t full[ERO_STAGES_MAX], empty[ERO_STAGES_MAX];
+    const int n_stages = a.n_stages;
     __shared__ float send_h[ERO_TILE], send_w[ERO_TILE];
     __shared__ bool s_last;
     bool cta_sent = false;
@@ -129,7 +150,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < ERO_STAGES; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
+        for (int s = 0; s < ERO_STAGES_MAX; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
         nxb_fence_mbar_init();
     }
     __syncthreads();
@@ -165,8 +186,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         int64_t tile = my_tiles > 0 ? tile_of(0) : 0;
         int64_t tile_next = my_tiles > 1 ? tile_of(1) : 0;
         if (my_tiles > 0 && lane < 16) word = __ldg(dw + tile * 16 + lane);
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            const int s = (int)(it % ERO_STAGES);
+        int s = 0;
+        uint32_t ph_empty = 1;                  // parity the empty barrier of stage s must have passed
+        for (int it = 0; it < (int)my_tiles; ++it) {
             const int64_t v0 = tile * ERO_TILE;
             const int32_t tile_id = (int32_t)tile;
             // descriptor words: 0..5 seg_start | 6..8 seg_len pairs | 9..11 seg_off pairs | 12 nseg | 13 irregular | 14 halo_used
@@ -177,6 +199,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int nseg = __shfl_sync(0xffffffffu, cur, 12);
             const int irregular = __shfl_sync(0xffffffffu, cur, 13);
             const int halo_used = __shfl_sync(0xffffffffu, cur, 14);
+            const int d3word = __shfl_sync(0xffffffffu, cur, 15);
+            const int kind = (a.dist3 == nullptr || irregular) ? 1 : (d3word & 0xff);   // 0: dist3, 1: full rows
+            const uint32_t d3_used = kind == 0 ? (uint32_t)(d3word >> 8) : 0u;
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
@@ -217,46 +242,75 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     halo_ready = true;
                 }
             }
-            nxb_mbar_wait(&empty[s], (uint32_t)(((it / ERO_STAGES) & 1) ^ 1));
+            nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
             if (lane == 0) {
                 st.irregular = irregular;
                 st.tile = tile_id;
+                st.kind = kind;
                 const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
-                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
+                const uint32_t dist_bytes = kind == 0 ? (uint32_t)(ERO_TILE * 12 + ERO_EXC * 24) + d3_used * 12u : (uint32_t)(ERO_TILE * 24);
+                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 12)) + dist_bytes + halo_bytes);
                 nxb_bulk_g2s(st.h, a.h_in + v0, ERO_TILE * 4, &full[s]);
                 nxb_bulk_g2s(st.w, a.w_in + v0, ERO_TILE * 4, &full[s]);
                 nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
-                nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
+                if (kind == 0) {
+                    nxb_bulk_g2s(st.dist, a.dist3 + v0 * 3, ERO_TILE * 12, &full[s]);
+                    nxb_bulk_g2s(st.exc, a.exc + (int64_t)tile_id * (ERO_EXC * 6), ERO_EXC * 24, &full[s]);
+                }
+                else           nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 nxb_bulk_g2s(st.adj, a.adj16 + v0 * 6, ERO_TILE * 12, &full[s]);
             } else if (q < nseg && !irregular) {
                 nxb_bulk_g2s(st.h + ERO_TILE + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
                 nxb_bulk_g2s(st.w + ERO_TILE + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+                if (seg_off < d3_used) {
+                    // dist3 rows of the (smaller-numbered) vertices of this run: owners of backward edges
+                    const uint32_t n3 = min(seg_len, d3_used - seg_off);
+                    nxb_bulk_g2s(st.dist + (ERO_TILE + seg_off) * 3, a.dist3 + (int64_t)seg_start * 3, n3 * 12u, &full[s]);
+                }
             }
             __syncwarp();
+            if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
         }
     } else {
         // ---------------- consumer warps: thread c owns vertex v0 + c of every tile of this CTA
         const int c = tid - 32;
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            const int s = (int)(it % ERO_STAGES);
-            nxb_mbar_wait(&full[s], (uint32_t)((it / ERO_STAGES) & 1));
+        int s = 0;
+        uint32_t ph_full = 0;
+        const bool sending = a.comm.send_ptr != nullptr;
+        const int n_early = a.comm.n_early;
+        for (int it = 0; it < (int)my_tiles; ++it) {
+            if (a.wait_ns == 0) nxb_mbar_wait(&full[s], ph_full);
+            else while (!nxb_mbar_try_wait(&full[s], ph_full)) __nanosleep(a.wait_ns);   // fewer spin instructions, less power
             const EroStage &st = stage[s];
             const int64_t tile = st.tile;
             const int64_t v = tile * (int64_t)ERO_TILE + c;
             float hn[6], wn[6], d[6];
-            {
+            const float me = st.h[c], wo = st.w[c], so = st.s[c];
+            const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
+            const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
+            const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
+            if (st.kind == 0 && !(code[0] & ERO_CODE_HEAVY)) {
+                // one stored length per edge: from this vertex's dist3 row, or from the row of the
+                // (smaller-numbered, staged) neighbour that owns the edge
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const uint32_t row = (code[q] & ERO_CODE_BACK) ? (code[q] & ERO_CODE_POS) : (uint32_t)c;
+                    d[q] = st.dist[row * 3 + ((code[q] >> ERO_CODE_I_SHIFT) & 3u)];
+                }
+            } else if (st.kind == 0) {
+                // skeleton-adjacent vertex: its full row travels with the tile (exception rows)
+                const float *ep = st.exc + ((code[0] >> ERO_CODE_EXC_SHIFT) & 3u) * 6;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) d[q] = ep[q];
+            } else {
                 const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
                 const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
                 d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
             }
-            const float me = st.h[c], wo = st.w[c], so = st.s[c];
             if (!st.irregular) {
-                const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
-                const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
-                const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
 #pragma unroll
-                for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q]]; wn[q] = st.w[code[q]]; }
+                for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q] & ERO_CODE_POS]; wn[q] = st.w[code[q] & ERO_CODE_POS]; }
             } else {
                 // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
                 const int64_t vv = v < a.n_own ? v : a.n_own - 1;
@@ -274,7 +328,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             float hh, ww, ss;
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
             if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
-            if (a.comm.send_ptr) {
+            if (sending) {
                 const int32_t e0 = __ldg(a.comm.send_ptr + tile), e1 = __ldg(a.comm.send_ptr + tile + 1);
                 if (e1 > e0) {                  // uniform over the 8 consumer warps
                     send_h[c] = hh; send_w[c] = ww;
@@ -288,8 +342,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     cta_sent = true;
                 }
             }
-            const int64_t slot = (int64_t)blockIdx.x + it * gridDim.x;
-            if (slot < a.comm.n_early && slot + gridDim.x >= a.comm.n_early) {
+            const int slot = (int)blockIdx.x + it * (int)gridDim.x;
+            if (slot < n_early && slot + (int)gridDim.x >= n_early) {
                 // this CTA's LAST boundary tile is done: all 8 consumer warps have read their inputs
                 // and stored to the peers.  One system fence per CTA (a fence per tile costs
                 // microseconds each while NVLink stores are in flight), then check in.
@@ -312,6 +366,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     }
                 }
             }
+            if (++s == n_stages) { s = 0; ph_full ^= 1u; }
         }
     }
 #ifdef NXB_ERO_DEBUG_WAIT
@@ -388,7 +443,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
     }
     EroTileDesc d;
     for (int k = 0; k < ERO_NSEG; ++k) { d.seg_start[k] = 0; d.seg_len[k] = 0; d.seg_off[k] = 0; }
-    d.nseg = 0; d.irregular = 0; d.halo_used = 0; d.pad = 0;
+    d.nseg = 0; d.irregular = 0; d.halo_used = 0; d.d3 = 0;
     const int BIG = 0x7fffffff;
     for (int k = 0; k <= ERO_NSEG; ++k) {
         int m = BIG;
@@ -415,6 +470,51 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         d.halo_used += len;
         d.nseg = k + 1;
     }
+    // ---- where each slot's edge length lives (dist3, see nxb_erosion_plan.cuh) ----
+    int d3_need = 0;                    // staged dist3 halo slots this vertex needs (0 = none)
+    bool is_heavy = false;
+    if (!d.irregular) {
+        bool heavy = false;
+        int fcnt = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            if (nb[q] < 0) continue;
+            if ((int64_t)nb[q] > v) { code[q] |= (uint32_t)(fcnt & 3) << ERO_CODE_I_SHIFT; ++fcnt; }
+            else {
+                // the neighbour n owns the edge: entry = rank of v among n's forward neighbours
+                const int64_t n = nb[q];
+                int fn = 0, idx = -1;
+                for (int t = 0; t < 6; ++t) {
+                    const int32_t m = adj[n * 6 + t];
+                    if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
+                }
+                if (fn > 3 || idx < 0) heavy = true;
+                else {
+                    code[q] |= ERO_CODE_BACK | (uint32_t)idx << ERO_CODE_I_SHIFT;
+                    const int pos = (int)(code[q] & ERO_CODE_POS);
+                    if (pos >= ERO_TILE) d3_need = max(d3_need, pos - ERO_TILE + 1);
+                }
+            }
+        }
+        if (fcnt > 3) heavy = true;
+        is_heavy = heavy;
+        if (heavy) d3_need = 0;
+    }
+    // exception row of a heavy vertex = number of heavy vertices before it in the tile
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, is_heavy);
+        __shared__ int wcount[ERO_TILE / 32];
+        if ((c & 31) == 0) wcount[c >> 5] = __popc(bal);
+        __syncthreads();
+        int before = __popc(bal & ((1u << (c & 31)) - 1u)), total = 0;
+        for (int w = 0; w < ERO_TILE / 32; ++w) { if (w < (c >> 5)) before += wcount[w]; total += wcount[w]; }
+        __syncthreads();
+        if (is_heavy) code[0] |= ERO_CODE_HEAVY | (uint32_t)(before & 3) << ERO_CODE_EXC_SHIFT;
+        if (total > ERO_EXC) d3_need = ERO_D3_CAP + 4;      // too many: the tile streams the full table
+    }
+    d3_need = -block_reduce_min(-d3_need, scratch);
+    d3_need = (d3_need + 3) & ~3;
+    d.d3 = d3_need > ERO_D3_CAP ? 1 : (d3_need << 8);
 #pragma unroll
     for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles
     if (c == 0) {
@@ -422,6 +522,64 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         if (d.irregular) atomicAdd(stats, 1);
         atomicMax(stats + 1, d.halo_used);
     }
+}
+
+// dist3[v][i] = length of the edge to v's i-th larger-numbered neighbour in slot order (rows with
+// more than 3 such neighbours -- the mesh skeleton -- are never referenced: see the plan's heavy bit)
+__global__ void __launch_bounds__(256)
+dist3_build_kernel(const int32_t *__restrict__ adj, const float *__restrict__ dist, int64_t n_own, int64_t n_rows,
+                   float *__restrict__ dist3)
+{
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_rows; v += (int64_t)gridDim.x * blockDim.x) {
+        float out[3] = {0.0f, 0.0f, 0.0f};
+        if (v < n_own) {
+            int f = 0;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int32_t n = adj[v * 6 + q];
+                if ((int64_t)n > v) { if (f < 3) out[f] = dist[v * 6 + q]; ++f; }
+            }
+        }
+        dist3[v * 3] = out[0]; dist3[v * 3 + 1] = out[1]; dist3[v * 3 + 2] = out[2];
+    }
+}
+
+// exception rows: the full 6 lengths of every heavy vertex, at [tile][row from the vertex's code]
+__global__ void __launch_bounds__(256)
+exc_build_kernel(const uint16_t *__restrict__ adj16, const float *__restrict__ dist, int64_t n_own, float *__restrict__ exc)
+{
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_own; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c0 = adj16[v * 6];
+        if (c0 & ERO_CODE_HEAVY) {
+            float *row = exc + (v / ERO_TILE) * (ERO_EXC * 6) + ((c0 >> ERO_CODE_EXC_SHIFT) & 3u) * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) row[q] = dist[v * 6 + q];
+        }
+    }
+}
+
+NXB_API int64_t nxb_erode_dist3_floats(int64_t n_own)
+{
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    return n_tiles * ERO_TILE * 3 + n_tiles * ERO_EXC * 6;
+}
+
+NXB_API int nxb_erode_dist3_build(const void *plan_mem, const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream)
+{
+    NXB_ARG(n_own >= 0);
+    if (n_own == 0) return NXB_OK;
+    NXB_ARG(plan_mem && adj && dist && dist3 && (((uintptr_t)dist3) & 15) == 0);
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE, n_rows = n_tiles * ERO_TILE;
+    const uint16_t *adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
+    float *exc = dist3 + n_rows * 3;
+    NXB_CUDA(cudaMemsetAsync(exc, 0, sizeof(float) * n_tiles * ERO_EXC * 6, (cudaStream_t)stream));
+    dist3_build_kernel<<<nxb_grid_resident(dist3_build_kernel, 256, 0, (n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        adj, dist, n_own, n_rows, dist3);
+    NXB_LAUNCH_CHECK();
+    exc_build_kernel<<<nxb_grid_resident(exc_build_kernel, 256, 0, (n_own + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        adj16, dist, n_own, exc);
+    NXB_LAUNCH_CHECK();
+    return NXB_OK;
 }
 
 NXB_API int64_t nxb_erode_plan_bytes(int64_t n_own)
@@ -455,7 +613,7 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
 
 static bool g_ero_attr_set[64] = {false};
 
-static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const float *dist,
+static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                               const float *h_in, const float *w_in, const float *s_in,
                               float *h_out, float *w_out, float *s_out,
                               int64_t n_own, float rain, const EroComm &comm, void *stream)
@@ -464,19 +622,28 @@ static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const fl
     if (n_own == 0) return NXB_OK;
     NXB_ARG(plan_mem && adj && dist && h_in && w_in && s_in && h_out && w_out && s_out);
     NXB_ARG(h_in != h_out && w_in != w_out && s_in != s_out);
-    NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
+    NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)dist3 | (uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
     const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
     EroPlanArgs a;
     a.desc = (const EroTileDesc *)plan_mem;
     a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
-    a.adj = adj; a.dist = dist;
+    a.adj = adj; a.dist = dist; a.dist3 = dist3;
+    a.exc = dist3 ? dist3 + n_tiles * ERO_TILE * 3 : nullptr;
     a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
     a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
     a.n_own = n_own; a.rain = rain;
     a.comm = comm;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
-    const size_t smem = sizeof(EroStage) * ERO_STAGES;
+    static int cfg_stages = 0, cfg_wait = -1;
+    if (cfg_stages == 0) {
+        const char *e = getenv("NXB_ERO_STAGES"), *w = getenv("NXB_ERO_WAIT_NS");
+        cfg_stages = e ? atoi(e) : 3;
+        if (cfg_stages < 2 || cfg_stages > ERO_STAGES_MAX) cfg_stages = 3;
+        cfg_wait = w ? atoi(w) : 0;
+    }
+    a.n_stages = cfg_stages; a.wait_ns = (unsigned)cfg_wait;
+    const size_t smem = sizeof(EroStage) * cfg_stages;
     if (dev < 64 && !g_ero_attr_set[dev]) {
         NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_ero_attr_set[dev] = true;
@@ -487,14 +654,14 @@ static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const fl
     return NXB_OK;
 }
 
-NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                                      const float *h_in, const float *w_in, const float *s_in,
                                      float *h_out, float *w_out, float *s_out,
                                      int64_t n_own, float rain, void *stream)
 {
     EroComm comm;
     memset(&comm, 0, sizeof comm);
-    return erode3_plan_launch(plan_mem, adj, dist, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
+    return erode3_plan_launch(plan_mem, adj, dist, dist3, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
 }
 
 // Sweep + halo exchange in ONE kernel (see EroComm).  send_ptr / send_entries: device CSR of
@@ -503,7 +670,7 @@ NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, c
 // for this rank); flags: this rank's flag array; wait_rank: host int32[n_wait] source ranks whose
 // flag must reach wait_target before halo slots are read; flag_value: raised in the peers when the
 // whole grid has finished; halo_begin: first halo slot; ticket: device uint32, zero.
-NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist,
+NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                                           const float *h_in, const float *w_in, const float *s_in,
                                           float *h_out, float *w_out, float *s_out,
                                           int64_t n_own, float rain,
@@ -533,7 +700,7 @@ NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *a
     comm.wait_target = wait_target; comm.flag_value = flag_value; comm.halo_begin = halo_begin;
     comm.tile_order = tile_order;
     comm.n_early = (int)n_early;
-    return erode3_plan_launch(plan_mem, adj, dist, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
+    return erode3_plan_launch(plan_mem, adj, dist, dist3, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

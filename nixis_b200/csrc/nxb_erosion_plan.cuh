@@ -12,13 +12,35 @@
 //     (-1 pads of valence-5 vertices point at the vertex itself, which contributes nothing).
 // A tile whose neighbours do not fit (more than ERO_NSEG segments or more than ERO_HALO_CAP halo
 // slots) is flagged irregular and processed with global gathers through the int32 table.
+//
+// EDGE LENGTHS ARE STORED ONCE PER EDGE (dist3).  The length of edge {a, b}, a < b, lives in the
+// row of a: dist3[a][i], i = rank of b among a's larger-numbered ("forward") neighbours in slot
+// order.  In the mesh interior every vertex has exactly 3 forward neighbours (next in its row, two
+// in the next row), so dist3 is float[V][3] -- half of the 6-per-vertex table.  The upper bits of
+// each 16-bit code say where the slot's length is:
+//     bits 10-11  i        entry of the owner's dist3 row
+//     bit  12     backward the owner is the NEIGHBOUR (staged: own tile or a halo run with smaller
+//                          indices, whose dist3 rows the producer stages as well)
+//     bit  15     (slot 0 only) heavy vertex: some edge has an owner with more than 3 forward
+//                          neighbours (mesh skeleton).  Its 6 lengths are copied into the tile's
+//                          exception rows (ERO_EXC per tile, staged with the tile); bits 13-14 of
+//                          slot 0 hold the row.  A tile with more heavy vertices is kind 1.
+// A regular tile whose backward halo positions exceed ERO_D3_CAP keeps streaming the full table
+// (kind 1).
 #pragma once
 #include <stdint.h>
 
 #define ERO_TILE 256
 #define ERO_NSEG 6
 #define ERO_MAXSEG 320          // longest single segment
-#define ERO_HALO_CAP 768        // halo slots per tile
+#define ERO_HALO_CAP 640        // halo slots per tile
+#define ERO_D3_CAP 296          // leading halo slots whose dist3 rows can be staged
+#define ERO_CODE_POS 0x03ffu
+#define ERO_CODE_I_SHIFT 10
+#define ERO_CODE_BACK 0x1000u
+#define ERO_CODE_HEAVY 0x8000u
+#define ERO_CODE_EXC_SHIFT 13
+#define ERO_EXC 4               // exception rows (6 lengths each) per tile
 #define ERO_STAGE_ELEMS (ERO_TILE + ERO_HALO_CAP)
 
 struct EroTileDesc {            // 64 bytes
@@ -28,6 +50,6 @@ struct EroTileDesc {            // 64 bytes
     int32_t nseg;
     int32_t irregular;
     int32_t halo_used;
-    int32_t pad;
+    int32_t d3;                 // bits 0-7: 0 = edge lengths from dist3, 1 = from the full table; bits 8..: staged dist3 halo slots
 };
 static_assert(sizeof(EroTileDesc) == 64, "EroTileDesc layout");

@@ -209,8 +209,9 @@ class ShardedErosion:
                 order = rt._ptr(self.tile_order) if os.environ.get("NXB_FUSED_TILE_ORDER") else None
             else:
                 self._await()
+            d3 = tp.dist3_for(self.dist)
             _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
-                      rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
+                      None if d3 is None else rt._ptr(d3), rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
                       tp.n_own, C.c_float(rain),
                       rt._ptr(self.send_ptr), rt._ptr(self.send_entries), len(self.send_peers), ph, pw, pf,
                       rt._ptr(self.flags), self._wait_rank, n_wait,

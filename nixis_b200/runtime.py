@@ -5,6 +5,7 @@ launches hand-written sm_100a kernels through `_lib`.  Nothing in this module co
 on the host; without a GPU or without the built library it raises.
 """
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
@@ -286,11 +287,26 @@ class ErosionPlan:
         stats = (C.c_int32 * 3)()
         _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
         self.n_tiles, self.n_irregular, self.max_halo = stats[0], stats[1], stats[2]
+        self._dist3 = {}
+
+    def dist3_for(self, dist):
+        """One-length-per-edge table derived from the full [n,6] table `dist` (built once, cached);
+        None unless NXB_ERO_DIST3=1: the sweep streams the full table by default, which measures
+        faster (590 us vs 715-750 us at d=2500; see the header of csrc/nxb_erosion.cu)."""
+        if os.environ.get("NXB_ERO_DIST3", "0") != "1":
+            return None
+        key = dist.data_ptr()
+        if key not in self._dist3:
+            d3 = torch.empty(_lib.load().nxb_erode_dist3_floats(self.n_own), dtype=F32, device=dist.device)
+            _lib.call("nxb_erode_dist3_build", _ptr(self.mem), _ptr(self.adj), _ptr(dist), self.n_own, _ptr(d3), _stream())
+            self._dist3 = {key: d3}
+        return self._dist3[key]
 
 
 def erode3_step(plan, dist, src, dst, rain):
     """src/dst: (h, w, s) tuples of float32 CUDA vectors of plan.capacity elements."""
-    _lib.call("nxb_erode3_plan_step_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist),
+    d3 = plan.dist3_for(dist)
+    _lib.call("nxb_erode3_plan_step_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist), None if d3 is None else _ptr(d3),
               _ptr(src[0]), _ptr(src[1]), _ptr(src[2]), _ptr(dst[0]), _ptr(dst[1]), _ptr(dst[2]),
               plan.n_own, C.c_float(rain), _stream())
 

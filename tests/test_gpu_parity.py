@@ -408,6 +408,31 @@ def test_erosion_large_single_step_vs_oracle(nx, oracle):
 
 
 # ---------------------------------------------------------------------------------- BASELINE configs
+@pytest.mark.parametrize("k", [40, 300, 700])
+def test_erosion_dist3_path_bit_identical_to_full_table(nx, monkeypatch, k):
+    """The sweep that streams one stored length per edge (dist3, 48 B/vertex) gives bit for bit what
+    the sweep streaming the full 6-per-vertex table (60 B/vertex) gives -- same values, same order."""
+    torch = nx.torch
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    h, _, _ = pipe.heights()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NXB_ERO_DIST3", mode)
+        st = pipe.erosion_state(h.clone())
+        st.run(12)
+        out[mode] = (st.heights.clone(), st.water.clone(), st.sediment.clone())
+    for a, b in zip(out["1"], out["0"]):
+        assert torch.equal(a, b)
+    assert bool(torch.isfinite(out["1"][0]).all())
+    plan = pipe._plan
+    d3 = plan.mem[: plan.n_tiles * 64].view(torch.int32).view(-1, 16)[:, 15]
+    irregular = plan.mem[: plan.n_tiles * 64].view(torch.int32).view(-1, 16)[:, 13]
+    fast = int(((d3 & 0xff) == 0).logical_and(irregular == 0).sum())
+    print(f"k={k}: {fast} of {plan.n_tiles} tiles stream dist3")
+    assert k < 300 or fast > 0.5 * plan.n_tiles
+
+
 def test_config2_d1000_fbm_assembly_erosion_vs_oracle(nx, oracle):
     """BASELINE configs[1..2] scale (d=1000, 10 000 002 vertices): fBm + assembly + 20 sweeps, device
     resident, against the float64 oracle on the same mesh."""

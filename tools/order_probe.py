@@ -16,7 +16,7 @@ def run(order, n=50):
     src, dst = st.cur, st.nxt
     def one():
         nonlocal src, dst
-        _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st.dist),
+        _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st.dist), None,
                   rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
                   tp.n_own, C.c_float(0.0), None, None, 0, None, None, None, None, None, 0,
                   C.c_uint32(0), C.c_uint32(0), 0, rt._ptr(ticket), None if order is None else rt._ptr(order), 0, rt._stream())
