@@ -201,7 +201,7 @@ def run_reference(args):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "ms_per_step is the d=2500 step time extrapolated from the bounded sample"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -234,7 +234,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     if world > 1:
         from nixis_b200.multigpu import run_multi_gpu_bench
-        return run_multi_gpu_bench(args, rank, world, local)
+        return run_multi_gpu_bench(args, rank, world, local, emit=emit)
 
     k, n_oct, iters = args.division, args.octaves, args.iters
     pipe = TerrainPipeline(k, seed=args.seed, n_octaves=n_oct, radius=1.0)
@@ -334,7 +334,7 @@ def run_ours(args):
         line["e2e"] = run_e2e(args, pipe, np, torch, rt, terrain, util, erosion)
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_reference_sample(n_oct, iters)
-    print(json.dumps(line))
+    emit(line)
 
 
 def pinned(np, torch, shape, dtype):
@@ -391,7 +391,27 @@ def run_e2e(args, pipe, np, torch, rt, terrain, util, erosion):
                    "with float64 numpy arrays (points / neighbours in pinned memory; every returned array is backed by pinned memory too)"}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Libraries write to stdout behind Python's back (NCCL prints "NCCL version ..." from C when the
+    # first communicator is created, whatever NCCL_DEBUG says).  Keep the original stdout for the
+    # result line only and send everything else -- Python prints included -- to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         return run_reference(args)

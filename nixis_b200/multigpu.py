@@ -304,7 +304,7 @@ class ShardedTerrain:
 
 
 # ---------------------------------------------------------------------------------------------
-def run_multi_gpu_bench(args, rank, world, local):
+def run_multi_gpu_bench(args, rank, world, local, emit=None):
     """bench.py --gpus N (N > 1): same step as the single-GPU arm, vertex range sharded over N ranks."""
     import json
     import statistics
@@ -407,4 +407,4 @@ def run_multi_gpu_bench(args, rank, world, local):
             "clocks": clocks, "gpu_launches": launches}
     if e2e is not None:
         line["e2e"] = e2e
-    print(json.dumps(line))
+    (emit or (lambda ln: print(json.dumps(ln))))(line)
