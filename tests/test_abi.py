@@ -100,3 +100,22 @@ def test_power_summary_combine_matches_sequential_scan(oracle):
             lo, hi = rt.power_bounds(rt.combine_power_summaries(summ), x.min(), x.max())
             _, stats = oracle.power_rescale(x, sel, 1, 1.0, return_stats=True)
             assert (lo, hi) == (stats[2], stats[3]), (x, sel, nshard)
+
+
+def test_swap_in_runner_reaches_our_create_mesh():
+    """tools/run_nixis.py pre-seeds sys.modules and executes the unmodified reference CLI: without a
+    GPU it must get as far as OUR create_mesh and fail loudly there (no CPU fallback).  Needs the
+    reference checkout (present in the build container only)."""
+    import subprocess
+    import sys
+    import torch
+    ref = os.environ.get("NIXIS_REF", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "nixis.py")):
+        pytest.skip("reference checkout not present")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run would go through")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_nixis.py"), "--ref", ref, "--",
+                        "-d", "4", "-s", "12345", "--novis"], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert "hot path swapped onto nixis_b200" in r.stdout
+    assert r.returncode != 0 and "nixis_b200 needs a CUDA device" in r.stderr
+    assert "nixis_b200/util.py" in r.stderr and "create_mesh" in r.stderr
