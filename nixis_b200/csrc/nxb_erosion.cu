@@ -47,8 +47,10 @@ struct __align__(128) EroStage {
     float exc[ERO_EXC * 6];             // kind 0: full rows of the tile's heavy vertices
     int32_t irregular;
     int32_t tile;
-    int32_t kind;                       // 0: dist holds dist3 rows, 1: full rows
-    int32_t pad[5];
+    int32_t kind;                       // 0: dist holds dist3 rows, 1: full rows, 2: affine tile (window layout, no codes)
+    int32_t pad0;
+    int32_t affk4[6];                   // kind 2: byte offset of slot q's neighbour relative to &h[c] / &w[c]
+    int32_t pad[30];
 };
 
 #define ERO_MAX_PEERS 8
@@ -93,6 +95,7 @@ struct EroPlanArgs {
     const float *dist;                                  // full table [.][6]
     const float *dist3;                                 // one entry per edge [.][3] (null: full table only)
     const float *exc;                                   // [n_tiles][ERO_EXC][6] rows of heavy vertices
+    int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
     unsigned wait_ns;                                   // consumers sleep this long between barrier polls (0: spin)
     const float *h_in, *w_in, *s_in;
@@ -185,28 +188,30 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         };
         int64_t tile = my_tiles > 0 ? tile_of(0) : 0;
         int64_t tile_next = my_tiles > 1 ? tile_of(1) : 0;
-        if (my_tiles > 0 && lane < 16) word = __ldg(dw + tile * 16 + lane);
+        if (my_tiles > 0) word = __ldg(dw + tile * ERO_DESC_WORDS + lane);
         int s = 0;
         uint32_t ph_empty = 1;                  // parity the empty barrier of stage s must have passed
         for (int it = 0; it < (int)my_tiles; ++it) {
             const int64_t v0 = tile * ERO_TILE;
             const int32_t tile_id = (int32_t)tile;
-            // descriptor words: 0..5 seg_start | 6..8 seg_len pairs | 9..11 seg_off pairs | 12 nseg | 13 irregular | 14 halo_used
+            // descriptor words: see ERO_DW_* (seg_start | seg_len pairs | seg_off pairs | nseg | irregular | halo_used | d3 | affine | K_q)
             const int32_t cur = word;
-            if (it + 1 < my_tiles && lane < 16) word = __ldg(dw + tile_next * 16 + lane);
+            if (it + 1 < my_tiles) word = __ldg(dw + tile_next * ERO_DESC_WORDS + lane);
             tile = tile_next;
             if (it + 2 < my_tiles) tile_next = tile_of(it + 2);
-            const int nseg = __shfl_sync(0xffffffffu, cur, 12);
-            const int irregular = __shfl_sync(0xffffffffu, cur, 13);
-            const int halo_used = __shfl_sync(0xffffffffu, cur, 14);
-            const int d3word = __shfl_sync(0xffffffffu, cur, 15);
-            const int kind = (a.dist3 == nullptr || irregular) ? 1 : (d3word & 0xff);   // 0: dist3, 1: full rows
+            const int nseg = __shfl_sync(0xffffffffu, cur, ERO_DW_NSEG);
+            const int irregular = __shfl_sync(0xffffffffu, cur, ERO_DW_IRREGULAR);
+            const int halo_used = __shfl_sync(0xffffffffu, cur, ERO_DW_HALO_USED);
+            const int d3word = __shfl_sync(0xffffffffu, cur, ERO_DW_D3);
+            const int affine = (a.use_affine && !irregular) ? __shfl_sync(0xffffffffu, cur, ERO_DW_AFFINE) : 0;
+            const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1), kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
+            const int kind = affine ? ERO_KIND_AFFINE : ((a.dist3 == nullptr || irregular) ? 1 : (d3word & 0xff));   // 0: dist3, 1: full rows
             const uint32_t d3_used = kind == 0 ? (uint32_t)(d3word >> 8) : 0u;
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
-            const uint32_t lens = (uint32_t)__shfl_sync(0xffffffffu, cur, 6 + (qq >> 1));
-            const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, 9 + (qq >> 1));
+            const uint32_t lens = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_LEN + (qq >> 1));
+            const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_OFF + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
             if (!halo_ready) {
@@ -244,7 +249,23 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             }
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
-            if (lane == 0) {
+            if (kind == ERO_KIND_AFFINE) {
+                // window layout: [v0 - 4, v0 + 260) of h and w, halo runs behind it; no adjacency codes
+                if (lane == 0) {
+                    st.irregular = 0; st.tile = tile_id; st.kind = kind;
+                    st.affk4[0] = (int)(int16_t)(kw0 & 0xffff) * 4; st.affk4[1] = (kw0 >> 16) * 4;
+                    st.affk4[2] = (int)(int16_t)(kw1 & 0xffff) * 4; st.affk4[3] = (kw1 >> 16) * 4;
+                    st.affk4[4] = (int)(int16_t)(kw2 & 0xffff) * 4; st.affk4[5] = (kw2 >> 16) * 4;
+                    nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_WIN * 8 + ERO_TILE * (4 + 24)) + (uint32_t)halo_used * 8u);
+                    nxb_bulk_g2s(st.h, a.h_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
+                    nxb_bulk_g2s(st.w, a.w_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
+                    nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
+                    nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
+                } else if (q < nseg) {
+                    nxb_bulk_g2s(st.h + ERO_WIN + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
+                    nxb_bulk_g2s(st.w + ERO_WIN + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+                }
+            } else if (lane == 0) {
                 st.irregular = irregular;
                 st.tile = tile_id;
                 st.kind = kind;
@@ -286,7 +307,22 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int64_t tile = st.tile;
             const int64_t v = tile * (int64_t)ERO_TILE + c;
             float hn[6], wn[6], d[6];
-            const float me = st.h[c], wo = st.w[c], so = st.s[c];
+            float me, wo, so;
+            if (st.kind == ERO_KIND_AFFINE) {
+                // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
+                const char *hb = reinterpret_cast<const char *>(st.h + c), *wb = reinterpret_cast<const char *>(st.w + c);
+                me = st.h[c + ERO_WIN_PAD]; wo = st.w[c + ERO_WIN_PAD]; so = st.s[c];
+                const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
+                const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
+                d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int k4 = st.affk4[q];
+                    hn[q] = *reinterpret_cast<const float *>(hb + k4);
+                    wn[q] = *reinterpret_cast<const float *>(wb + k4);
+                }
+            } else {
+            me = st.h[c]; wo = st.w[c]; so = st.s[c];
             const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
             const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
             const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
@@ -322,6 +358,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
                     hn[q] = __ldg(a.h_in + n); wn[q] = __ldg(a.w_in + n);
                 }
+            }
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nxb_smem_u32(&empty[s])) : "memory");
@@ -457,10 +494,28 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         // before and just after the tile must not be merged into one segment spanning it)
         int wend = s + ERO_MAXSEG;
         if (s < v0 && wend > v0) wend = (int)v0;
-        int e = -1;                                                             // largest open index inside the window
+        // The run ends at the first gap of more than ERO_GAP unneeded elements: without this the
+        // element just after the tile and the start of the next mesh row, ~60..320 indices apart on
+        // rows of 260..580 vertices, were merged into one 320-slot window, the halo area overflowed
+        // and a fifth of the tiles at d = 1000 fell back to global gathers.
+        __shared__ unsigned occ[ERO_MAXSEG / 32];
+        __shared__ int e_sh;
+        if (c < ERO_MAXSEG / 32) occ[c] = 0u;
+        __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 6; ++q) if (open[q] && nb[q] < wend) e = max(e, nb[q]);
-        e = -block_reduce_min(-e, scratch);
+        for (int q = 0; q < 6; ++q)
+            if (open[q] && nb[q] >= s && nb[q] < wend) atomicOr(&occ[(nb[q] - s) >> 5], 1u << ((nb[q] - s) & 31));
+        __syncthreads();
+        if (c == 0) {
+            int last = m - s, gap = 0;
+            for (int i = m - s + 1; i < wend - s; ++i) {
+                if (occ[i >> 5] >> (i & 31) & 1u) { last = i; gap = 0; }
+                else if (++gap > ERO_GAP) break;
+            }
+            e_sh = s + last;
+        }
+        __syncthreads();
+        const int e = e_sh;                                                     // last needed index of the run
         const int len = ((e + 1 - s) + 3) & ~3;
         if (d.halo_used + len > ERO_HALO_CAP || (int64_t)s + len > capacity) { d.irregular = 1; break; }
 #pragma unroll
@@ -515,10 +570,35 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
     d3_need = -block_reduce_min(-d3_need, scratch);
     d3_need = (d3_need + 3) & ~3;
     d.d3 = d3_need > ERO_D3_CAP ? 1 : (d3_need << 8);
+    // ---- implicit adjacency: is the staging index of every slot's neighbour c + K_q for all c? ----
+    {
+        __shared__ int k0[6];
+        int kq[6];
+        bool ok = !d.irregular && v < n_own && v0 >= ERO_WIN_PAD && v0 + ERO_TILE + ERO_WIN_PAD <= capacity &&
+                  ERO_WIN + d.halo_used <= ERO_STAGE_ELEMS;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int64_t n = nb[q];
+            if (n < 0) { ok = false; kq[q] = 0; continue; }
+            int widx;
+            if (n >= v0 - ERO_WIN_PAD && n < v0 + ERO_TILE + ERO_WIN_PAD) widx = (int)(n - v0) + ERO_WIN_PAD;
+            else widx = ERO_WIN + ((int)(code[q] & ERO_CODE_POS) - ERO_TILE);
+            kq[q] = widx - c;
+        }
+        if (c == 0) for (int q = 0; q < 6; ++q) k0[q] = kq[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ok = ok && kq[q] == k0[q];
+        const int all_ok = __syncthreads_and(ok ? 1 : 0);
+        d.affine = all_ok;
+        for (int q = 0; q < 6; ++q) d.aff_k[q] = (int16_t)(all_ok ? k0[q] : 0);
+        for (int t = 0; t < 8; ++t) d.pad[t] = 0;
+    }
 #pragma unroll
     for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles
     if (c == 0) {
         desc[tile] = d;
+        if (d.affine) atomicAdd(stats + 2, 1);
         if (d.irregular) atomicAdd(stats, 1);
         atomicMax(stats + 1, d.halo_used);
     }
@@ -599,15 +679,15 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
     EroTileDesc *desc = (EroTileDesc *)plan_mem;
     uint16_t *adj16 = (uint16_t *)((char *)plan_mem + n_tiles * sizeof(EroTileDesc));
     int32_t *stats = nullptr;
-    NXB_CUDA(cudaMalloc(&stats, 8));
-    NXB_CUDA(cudaMemsetAsync(stats, 0, 8, st));
+    NXB_CUDA(cudaMalloc(&stats, 12));
+    NXB_CUDA(cudaMemsetAsync(stats, 0, 12, st));
     ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats);
     NXB_LAUNCH_CHECK();
-    int32_t h[2] = {0, 0};
-    NXB_CUDA(cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, st));
+    int32_t h[3] = {0, 0, 0};
+    NXB_CUDA(cudaMemcpyAsync(h, stats, 12, cudaMemcpyDeviceToHost, st));
     NXB_CUDA(cudaStreamSynchronize(st));
     NXB_CUDA(cudaFree(stats));
-    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; }
+    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; stats_host[3] = h[2]; }
     return NXB_OK;
 }
 
@@ -643,6 +723,7 @@ static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const fl
         cfg_wait = w ? atoi(w) : 0;
     }
     a.n_stages = cfg_stages; a.wait_ns = (unsigned)cfg_wait;
+    { const char *e = getenv("NXB_ERO_AFFINE"); a.use_affine = e ? atoi(e) : 1; }      // read per launch: tests toggle it
     const size_t smem = sizeof(EroStage) * cfg_stages;
     if (dev < 64 && !g_ero_attr_set[dev]) {
         NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

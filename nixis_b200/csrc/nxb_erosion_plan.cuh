@@ -31,8 +31,9 @@
 #include <stdint.h>
 
 #define ERO_TILE 256
-#define ERO_NSEG 6
+#define ERO_NSEG 8
 #define ERO_MAXSEG 320          // longest single segment
+#define ERO_GAP 16              // a run of needed indices ends at a longer gap
 #define ERO_HALO_CAP 640        // halo slots per tile
 #define ERO_D3_CAP 296          // leading halo slots whose dist3 rows can be staged
 #define ERO_CODE_POS 0x03ffu
@@ -43,7 +44,20 @@
 #define ERO_EXC 4               // exception rows (6 lengths each) per tile
 #define ERO_STAGE_ELEMS (ERO_TILE + ERO_HALO_CAP)
 
-struct EroTileDesc {            // 64 bytes
+// IMPLICIT ADJACENCY (kind 2).  Away from the mesh skeleton and from row ends the neighbours of
+// vertex v0 + c sit at FIXED distances: c - 1, c + 1, and four positions in the rows above / below.
+// For such an "affine" tile the staging index of slot q's neighbour is c + K_q with six per-tile
+// constants K_q, provided the tile's own values are staged as the 264-element window
+// [v0 - 4, v0 + 260) (vertex c at window index c + 4, so the elements just before / after the tile
+// are ordinary window entries) followed by the halo runs at index ERO_WIN.  The sweep then needs no
+// per-vertex adjacency at all: the 12 B/vertex code stream is not read (48 B per vertex-sweep) and
+// the per-vertex code unpacking disappears.  The plan marks a tile affine when all 256 vertices
+// are valid, have six neighbours, and agree on every K_q.
+#define ERO_WIN_PAD 4
+#define ERO_WIN (ERO_TILE + 2 * ERO_WIN_PAD)     // 264
+#define ERO_KIND_AFFINE 2
+
+struct EroTileDesc {            // 128 bytes
     int32_t seg_start[ERO_NSEG];
     uint16_t seg_len[ERO_NSEG];
     uint16_t seg_off[ERO_NSEG]; // offset of the segment inside the halo area
@@ -51,5 +65,18 @@ struct EroTileDesc {            // 64 bytes
     int32_t irregular;
     int32_t halo_used;
     int32_t d3;                 // bits 0-7: 0 = edge lengths from dist3, 1 = from the full table; bits 8..: staged dist3 halo slots
+    int32_t affine;             // 1: implicit adjacency, aff_k valid
+    int16_t aff_k[6];           // K_q: staging index of slot q's neighbour minus c (window layout)
+    int32_t pad[8];
 };
-static_assert(sizeof(EroTileDesc) == 64, "EroTileDesc layout");
+static_assert(sizeof(EroTileDesc) == 128, "EroTileDesc layout");
+#define ERO_DESC_WORDS 32
+// word indices of the descriptor fields (the producer warp holds one word per lane)
+#define ERO_DW_LEN (ERO_NSEG)
+#define ERO_DW_OFF (ERO_NSEG + ERO_NSEG / 2)
+#define ERO_DW_NSEG (2 * ERO_NSEG)
+#define ERO_DW_IRREGULAR (2 * ERO_NSEG + 1)
+#define ERO_DW_HALO_USED (2 * ERO_NSEG + 2)
+#define ERO_DW_D3 (2 * ERO_NSEG + 3)
+#define ERO_DW_AFFINE (2 * ERO_NSEG + 4)
+#define ERO_DW_AFFK (2 * ERO_NSEG + 5)

@@ -123,9 +123,10 @@ class ShardedErosion:
         self.send_ptr = ptr.to(torch.int32).contiguous()
         self._wait_rank = (C.c_int32 * max(1, len(self.recv_peers)))(*self.recv_peers)
         # processing order: tiles that read halo slots (a halo segment, or irregular) go last
-        desc = self.tile_plan.mem[: n_tiles * 64].view(torch.int32).view(n_tiles, 16)
-        seg_start, nseg, irregular = desc[:, 0:6].to(torch.int64), desc[:, 12:13], desc[:, 13]
-        live = torch.arange(6, device=dev).unsqueeze(0) < nseg
+        desc = self.tile_plan.mem[: n_tiles * 128].view(torch.int32).view(n_tiles, 32)
+        NSEG = 8                      # nxb_erosion_plan.cuh: seg_start | seg_len | seg_off | nseg | irregular | ...
+        seg_start, nseg, irregular = desc[:, 0:NSEG].to(torch.int64), desc[:, 2 * NSEG:2 * NSEG + 1], desc[:, 2 * NSEG + 1]
+        live = torch.arange(NSEG, device=dev).unsqueeze(0) < nseg
         needs_halo = ((seg_start >= plan.n_own_pad) & live).any(dim=1) | (irregular != 0)
         self.tile_order = torch.argsort(needs_halo.to(torch.int8), stable=True).to(torch.int32).contiguous()
         self.n_halo_tiles = int(needs_halo.sum().item())

@@ -252,6 +252,7 @@ def adj_sort(adj):
 
 
 ERO_TILE = 256
+ERO_DESC_BYTES, ERO_DESC_WORDS = 128, 32
 
 
 def round_up(n, m):
@@ -284,9 +285,9 @@ class ErosionPlan:
         self.capacity = round_up(self.n_own, ERO_TILE) if capacity is None else int(capacity)
         nbytes = _lib.load().nxb_erode_plan_bytes(self.n_own)
         self.mem = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=adj.device)
-        stats = (C.c_int32 * 3)()
+        stats = (C.c_int32 * 4)()
         _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
-        self.n_tiles, self.n_irregular, self.max_halo = stats[0], stats[1], stats[2]
+        self.n_tiles, self.n_irregular, self.max_halo, self.n_affine = stats[0], stats[1], stats[2], stats[3]
         self._dist3 = {}
 
     def dist3_for(self, dist):

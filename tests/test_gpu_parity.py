@@ -417,6 +417,7 @@ def test_erosion_dist3_path_bit_identical_to_full_table(nx, monkeypatch, k):
     pipe.build_mesh()
     h, _, _ = pipe.heights()
     out = {}
+    monkeypatch.setenv("NXB_ERO_AFFINE", "0")
     for mode in ("1", "0"):
         monkeypatch.setenv("NXB_ERO_DIST3", mode)
         st = pipe.erosion_state(h.clone())
@@ -426,11 +427,32 @@ def test_erosion_dist3_path_bit_identical_to_full_table(nx, monkeypatch, k):
         assert torch.equal(a, b)
     assert bool(torch.isfinite(out["1"][0]).all())
     plan = pipe._plan
-    d3 = plan.mem[: plan.n_tiles * 64].view(torch.int32).view(-1, 16)[:, 15]
-    irregular = plan.mem[: plan.n_tiles * 64].view(torch.int32).view(-1, 16)[:, 13]
+    d3 = plan.mem[: plan.n_tiles * 128].view(torch.int32).view(-1, 32)[:, 19]
+    irregular = plan.mem[: plan.n_tiles * 128].view(torch.int32).view(-1, 32)[:, 17]
     fast = int(((d3 & 0xff) == 0).logical_and(irregular == 0).sum())
     print(f"k={k}: {fast} of {plan.n_tiles} tiles stream dist3")
     assert k < 300 or fast > 0.5 * plan.n_tiles
+
+
+@pytest.mark.parametrize("k", [40, 300, 700, 1000])
+def test_erosion_implicit_adjacency_bit_identical(nx, monkeypatch, k):
+    """Tiles whose neighbours sit at per-tile constant distances are swept without reading any
+    adjacency codes (48 B/vertex); the result is bit for bit the one of the explicit-code path."""
+    torch = nx.torch
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    h, _, _ = pipe.heights()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NXB_ERO_AFFINE", mode)
+        st = pipe.erosion_state(h.clone())
+        st.run(12)
+        out[mode] = (st.heights.clone(), st.water.clone(), st.sediment.clone())
+    for a, b in zip(out["1"], out["0"]):
+        assert torch.equal(a, b)
+    plan = pipe._plan
+    print(f"k={k}: {plan.n_affine} of {plan.n_tiles} tiles use implicit adjacency")
+    assert k < 700 or plan.n_affine > 0.15 * plan.n_tiles
 
 
 def test_config2_d1000_fbm_assembly_erosion_vs_oracle(nx, oracle):

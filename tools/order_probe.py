@@ -29,7 +29,11 @@ def run(order, n=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 ident = torch.arange(n_tiles, dtype=torch.int32, device="cuda")
-print(f"k={k} tiles={n_tiles}")
+print(f"k={k} tiles={n_tiles} affine={tp.n_affine} irregular={tp.n_irregular}")
+for aff in ("1", "0", "1", "0"):
+    os.environ["NXB_ERO_AFFINE"] = aff
+    print(f"NXB_ERO_AFFINE={aff}: {run(None):.1f} us")
+sys.exit(0)
 print("null order        :", round(run(None), 1), "us")
 print("identity order    :", round(run(ident), 1), "us")
 mask = (torch.arange(n_tiles, device="cuda") % 5 == 0)
