@@ -136,6 +136,9 @@ __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i
     if (ss > cw) { hh += ss - cw; ss -= ss - cw; }
 }
 
+// COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop
+// (the sweep is issue-co-limited: each instruction per vertex counts).
+template <bool COMM>
 __global__ void __launch_bounds__(ERO_THREADS)
 erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 {
@@ -170,8 +173,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
         const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
         int32_t word = 0;                       // this lane's word of the 16-word descriptor
-        bool halo_ready = a.comm.n_wait == 0;
-        const int32_t *order = a.comm.tile_order;
+        bool halo_ready = !COMM || a.comm.n_wait == 0;
+        const int32_t *order = COMM ? a.comm.tile_order : nullptr;
         // order lookups are batched: lane l holds the entry of iteration 32 b + l, the next batch is
         // already in flight.  (One dependent __ldg per tile in front of the descriptor load made the
         // producer latency-bound: +30% per sweep.)  tile_of is called with i = 0, 1, 2, ... in turn.
@@ -298,8 +301,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const int c = tid - 32;
         int s = 0;
         uint32_t ph_full = 0;
-        const bool sending = a.comm.send_ptr != nullptr;
-        const int n_early = a.comm.n_early;
+        const bool sending = COMM && a.comm.send_ptr != nullptr;
+        const int n_early = COMM ? a.comm.n_early : 0;
         for (int it = 0; it < (int)my_tiles; ++it) {
             if (a.wait_ns == 0) nxb_mbar_wait(&full[s], ph_full);
             else while (!nxb_mbar_try_wait(&full[s], ph_full)) __nanosleep(a.wait_ns);   // fewer spin instructions, less power
@@ -380,7 +383,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 }
             }
             const int slot = (int)blockIdx.x + it * (int)gridDim.x;
-            if (slot < n_early && slot + (int)gridDim.x >= n_early) {
+            if (COMM && slot < n_early && slot + (int)gridDim.x >= n_early) {
                 // this CTA's LAST boundary tile is done: all 8 consumer warps have read their inputs
                 // and stored to the peers.  One system fence per CTA (a fence per tile costs
                 // microseconds each while NVLink stores are in flight), then check in.
@@ -417,7 +420,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 3] = (unsigned)((c1 - dbg_c0) * 1000 / (long long)(t1 - dbg_t0 + 1));
     }
 #endif
-    if (a.comm.n_send_peers > 0 && a.comm.n_early == 0) {
+    if (COMM && a.comm.n_send_peers > 0 && a.comm.n_early == 0) {
         // every peer store of this CTA is visible system-wide before the CTA checks in; the last
         // CTA of the grid then raises this rank's flag in every peer
         if (cta_sent) __threadfence_system();
@@ -726,11 +729,18 @@ static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const fl
     { const char *e = getenv("NXB_ERO_AFFINE"); a.use_affine = e ? atoi(e) : 1; }      // read per launch: tests toggle it
     const size_t smem = sizeof(EroStage) * cfg_stages;
     if (dev < 64 && !g_ero_attr_set[dev]) {
-        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_ero_attr_set[dev] = true;
     }
-    int grid = nxb_grid_resident(erode3_plan_kernel, ERO_THREADS, smem, n_tiles);
-    erode3_plan_kernel<<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
+    const bool use_comm = comm.n_send_peers > 0 || comm.n_wait > 0 || comm.tile_order != nullptr || comm.ticket != nullptr;
+    if (use_comm) {
+        int grid = nxb_grid_resident(erode3_plan_kernel<true>, ERO_THREADS, smem, n_tiles);
+        erode3_plan_kernel<true><<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        int grid = nxb_grid_resident(erode3_plan_kernel<false>, ERO_THREADS, smem, n_tiles);
+        erode3_plan_kernel<false><<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }

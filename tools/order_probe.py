@@ -30,9 +30,20 @@ def run(order, n=50):
     return e0.elapsed_time(e1) / n * 1e3
 ident = torch.arange(n_tiles, dtype=torch.int32, device="cuda")
 print(f"k={k} tiles={n_tiles} affine={tp.n_affine} irregular={tp.n_irregular}")
-for aff in ("1", "0", "1", "0"):
+def run_plain(n=50):
+    src, dst = st.cur, st.nxt
+    for _ in range(5):
+        rt.erode3_step(tp, st.dist, src, dst, 0.0); src, dst = dst, src
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        rt.erode3_step(tp, st.dist, src, dst, 0.0); src, dst = dst, src
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for aff in ("1", "0", "1"):
     os.environ["NXB_ERO_AFFINE"] = aff
-    print(f"NXB_ERO_AFFINE={aff}: {run(None):.1f} us")
+    print(f"NXB_ERO_AFFINE={aff}: single-GPU kernel {run_plain():.1f} us, exchange-capable kernel {run(None):.1f} us")
 sys.exit(0)
 print("null order        :", round(run(None), 1), "us")
 print("identity order    :", round(run(ident), 1), "us")
