@@ -1,9 +1,11 @@
 // Erosion sweeps -- erosion.py:34-40, 76-99, 197-279 -- as a shared-memory-staged stencil.
 //
-// HBM-bound.  Algorithmic traffic per vertex-iteration of erosion_iteration3:
+// Bound by HBM and by consumer instruction issue at the same time (profiles/r01_ncu_*).
+// Algorithmic traffic per vertex-iteration of erosion_iteration3:
 //   own h,w,s read 12 B + write 12 B + adjacency row 24 B + own position 12 B = 60 B.
 // What this implementation actually streams per vertex-iteration:
-//   h,w,s read 12 B + write 12 B + 16-bit tile-local adjacency 12 B + 6 edge lengths 24 B = 60 B.
+//   h,w,s read 12 B + write 12 B + 6 edge lengths 24 B = 48 B on affine tiles (implicit adjacency,
+//   ~80 % of the tiles at d = 2500), + 12 B of 16-bit tile-local adjacency on the other tiles.
 //
 // History (profiles/r01_ncu_summary.json): v1, one thread per vertex with 18 global gathers
 // (xyz, h, w of 6 neighbours), ran at 45 % of HBM peak with minimal DRAM traffic -- latency bound;
@@ -16,12 +18,15 @@
 //     sqrt is evaluated in the sweep; it also removes the cancellation error of differencing FP32
 //     positions (relative 1e-4 at d=2500).
 //   * TILE PLAN (nxb_erosion_plan.cuh): for each tile of 256 consecutive vertices the neighbours
-//     are the tile itself plus <= 6 contiguous index runs (mesh rows above / below, the elements
+//     are the tile itself plus <= 8 contiguous index runs (mesh rows above / below, the elements
 //     next to the tile ends).  A producer warp brings the tile's own streams AND those runs of
 //     h / w into shared memory with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an
 //     mbarrier, n_stages tiles ahead; eight consumer warps then read every neighbour value from
 //     shared memory through a 16-bit tile-local adjacency.  No global gathers, no L1 dependence.
 //     The halo runs were just streamed by a neighbouring tile, so they come from L2, not HBM.
+//   * IMPLICIT ADJACENCY (nxb_erosion_plan.cuh, kind 2): tiles whose six neighbour distances are the
+//     same for all 256 vertices are staged as a 264-element window + halo runs and swept without any
+//     adjacency codes: -12 B and -27 instructions per vertex, 0.59 -> 0.51-0.56 ms per sweep at d=2500.
 //   * ONE LENGTH PER EDGE (dist3, nxb_erosion_plan.cuh) is implemented and bit-identical, but OFF by
 //     default: it cuts the DRAM reads from 3.16 GB to 2.53 GB per sweep at d = 2500 (ncu) and still
 //     runs 715-750 us against 590 us, because at 590 us the consumer warps are already issue-bound
