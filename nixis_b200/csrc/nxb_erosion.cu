@@ -102,7 +102,6 @@ struct EroPlanArgs {
     const float *exc;                                   // [n_tiles][ERO_EXC][6] rows of heavy vertices
     int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
-    unsigned wait_ns;                                   // consumers sleep this long between barrier polls (0: spin)
     const float *h_in, *w_in, *s_in;
     float *h_out, *w_out, *s_out;
     int64_t n_own;
@@ -309,8 +308,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const bool sending = COMM && a.comm.send_ptr != nullptr;
         const int n_early = COMM ? a.comm.n_early : 0;
         for (int it = 0; it < (int)my_tiles; ++it) {
-            if (a.wait_ns == 0) nxb_mbar_wait(&full[s], ph_full);
-            else while (!nxb_mbar_try_wait(&full[s], ph_full)) __nanosleep(a.wait_ns);   // fewer spin instructions, less power
+            nxb_mbar_wait(&full[s], ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
             const EroStage &st = stage[s];
             const int64_t tile = st.tile;
             const int64_t v = tile * (int64_t)ERO_TILE + c;
@@ -723,14 +721,13 @@ static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const fl
     a.comm = comm;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
-    static int cfg_stages = 0, cfg_wait = -1;
+    static int cfg_stages = 0;
     if (cfg_stages == 0) {
-        const char *e = getenv("NXB_ERO_STAGES"), *w = getenv("NXB_ERO_WAIT_NS");
+        const char *e = getenv("NXB_ERO_STAGES");
         cfg_stages = e ? atoi(e) : 3;
         if (cfg_stages < 2 || cfg_stages > ERO_STAGES_MAX) cfg_stages = 3;
-        cfg_wait = w ? atoi(w) : 0;
     }
-    a.n_stages = cfg_stages; a.wait_ns = (unsigned)cfg_wait;
+    a.n_stages = cfg_stages;
     { const char *e = getenv("NXB_ERO_AFFINE"); a.use_affine = e ? atoi(e) : 1; }      // read per launch: tests toggle it
     const size_t smem = sizeof(EroStage) * cfg_stages;
     if (dev < 64 && !g_ero_attr_set[dev]) {

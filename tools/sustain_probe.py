@@ -24,5 +24,5 @@ e0.record(); st.run(n); e1.record(); torch.cuda.synchronize()
 stop = True; t.join()
 ms = e0.elapsed_time(e1)
 mid = clk[len(clk)//4:] or [(0, 0)]
-print(f"stages={os.environ.get('NXB_ERO_STAGES','3')} wait_ns={os.environ.get('NXB_ERO_WAIT_NS','0')}: {ms/n*1e3:.1f} us/sweep over {n} sweeps; "
+print(f"stages={os.environ.get('NXB_ERO_STAGES','3')}: {ms/n*1e3:.1f} us/sweep over {n} sweeps; "
       f"SM {sorted(c for c,_ in mid)[len(mid)//2]:.0f} MHz, {max(p for _,p in mid):.0f} W")
