@@ -223,7 +223,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
             if (!halo_ready) {
                 // does this tile read halo slots?  (a segment in the halo area, or global gathers)
-                const bool mine = (q >= 0 && q < nseg && (int64_t)seg_start >= a.comm.halo_begin) || irregular;
+                // (an affine tile reads the 4 elements after its end through its window, not a run)
+                const bool mine = (q >= 0 && q < nseg && (int64_t)seg_start >= a.comm.halo_begin) || irregular ||
+                                  (affine && v0 + ERO_TILE + ERO_WIN_PAD > a.comm.halo_begin);
                 if (__any_sync(0xffffffffu, mine)) {
                     if (lane < a.comm.n_wait) {
                         const volatile uint32_t *f = a.comm.flags + a.comm.wait_rank[lane];

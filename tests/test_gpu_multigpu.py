@@ -18,10 +18,10 @@ def test_sharded_bit_identical_to_single_gpu(world):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, found {torch.cuda.device_count()}")
-    env = dict(os.environ, MGPU_SKIP_TIMING="1", MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MGPU_SKIP_TIMING="1", MASTER_ADDR="127.0.0.1", MGPU_CHECK_K="700")   # k=700: most tiles affine
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     ok = [ln for ln in r.stdout.splitlines() if "bit-identical h/w/s = (True, True, True)" in ln]
-    assert len(ok) == 6, r.stdout[-2000:]          # 3 transports x 2 mesh sizes
+    assert len(ok) == 9, r.stdout[-2000:]          # 3 transports x 3 mesh sizes

@@ -23,7 +23,7 @@ def gather_own(t, terr):
 
 TRANSPORTS = os.environ.get("MGPU_TRANSPORTS", "fused,nvlink,p2p").split(",")
 for transport in TRANSPORTS:
-    for k, sweeps in ((64, 25), (200, 10)):
+    for k, sweeps in ((64, 25), (200, 10)) + (((int(os.environ["MGPU_CHECK_K"]), 6),) if os.environ.get("MGPU_CHECK_K") else ()):
         terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
         h, ocean, lvl = terr.heights()
         terr.erosion.load(h)
