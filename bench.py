@@ -297,7 +297,7 @@ def run_ours(args):
     fbm_tflops = FLOP_PER_VERT_OCT * V * n_oct / (fbm_ms * 1e-3) / 1e12
     roofline = {"kernel": "erode3_plan_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ero_gbs / hbm_peak,
-                "traffic": ncu_traffic("r1e_erode3_v5_affine_d2500") if k == 2500 else None,
+                "traffic": ncu_traffic("r1f_erode3_v5_final_d2500") if k == 2500 else None,
                 "traffic_source": "profiles/r01_ncu_summary.json (ncu --set full, same kernel, d=2500, bytes per launch)",
                 "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_VERT_ITER * V, "avg_launch_ms": ero_launch_ms,
