@@ -469,7 +469,7 @@ __device__ __forceinline__ int block_reduce_min(int v, int *scratch)
 
 __global__ void __launch_bounds__(ERO_TILE)
 ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity,
-                EroTileDesc *__restrict__ desc, uint16_t *__restrict__ adj16, int32_t *__restrict__ stats)
+                EroTileDesc *__restrict__ desc, uint16_t *__restrict__ adj16, int32_t *__restrict__ stats, int want_d3)
 {
     __shared__ int scratch[ERO_TILE / 32];
     const int64_t tile = blockIdx.x, v0 = tile * ERO_TILE;
@@ -536,7 +536,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
     // ---- where each slot's edge length lives (dist3, see nxb_erosion_plan.cuh) ----
     int d3_need = 0;                    // staged dist3 halo slots this vertex needs (0 = none)
     bool is_heavy = false;
-    if (!d.irregular) {
+    if (!d.irregular && want_d3) {      // 36 scattered reads per vertex: only when the dist3 sweep is asked for
         bool heavy = false;
         int fcnt = 0;
 #pragma unroll
@@ -577,7 +577,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
     }
     d3_need = -block_reduce_min(-d3_need, scratch);
     d3_need = (d3_need + 3) & ~3;
-    d.d3 = d3_need > ERO_D3_CAP ? 1 : (d3_need << 8);
+    d.d3 = (!want_d3 || d3_need > ERO_D3_CAP) ? 1 : (d3_need << 8);
     // ---- implicit adjacency: is the staging index of every slot's neighbour c + K_q for all c? ----
     {
         __shared__ int k0[6];
@@ -689,7 +689,8 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
     int32_t *stats = nullptr;
     NXB_CUDA(cudaMalloc(&stats, 12));
     NXB_CUDA(cudaMemsetAsync(stats, 0, 12, st));
-    ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats);
+    const char *d3env = getenv("NXB_ERO_DIST3");
+    ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats, d3env && atoi(d3env) == 1);
     NXB_LAUNCH_CHECK();
     int32_t h[3] = {0, 0, 0};
     NXB_CUDA(cudaMemcpyAsync(h, stats, 12, cudaMemcpyDeviceToHost, st));
