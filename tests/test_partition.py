@@ -125,3 +125,24 @@ def test_sharded_erosion_bit_identical_gloo(world, oracle):
         ok, b, e, hh, ww, ss = out[r]
         assert ok
         assert np.array_equal(hh, h[b:e]) and np.array_equal(ww, wat[b:e]) and np.array_equal(ss, sed[b:e])
+
+
+@pytest.mark.parametrize("V,world,front,cost", [(62500002, 8, 74982, 6.0), (10000002, 4, 29982, 6.0), (1024002, 3, 9582, 1.0),
+                                                (162, 4, 42, 6.0), (12, 3, 12, 6.0)])
+def test_vertex_ranges_cost_weighted(V, world, front, cost):
+    """Ranges are contiguous, tile-aligned, cover [0, V) and equalise COST when the first `front`
+    vertices (the mesh skeleton) are `cost` times as expensive as the rest."""
+    r = P.vertex_ranges(V, world, front=front, front_cost=cost)
+    assert len(r) == world and r[0][0] == 0 and r[-1][1] == V
+    assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+    assert all(b % P.TILE == 0 or b == V for b, _ in r) and all(e >= b for b, e in r)
+
+    def weight(b, e):
+        f = max(0, min(e, front) - min(b, front))
+        return f * cost + (e - b - f)
+    w = [weight(b, e) for b, e in r]
+    if V > 100 * P.TILE * world:
+        assert max(w) - min(w) <= 2 * P.TILE * cost + V % P.TILE + P.TILE * world     # equal up to tile rounding
+        if cost > 1:
+            assert r[0][1] - r[0][0] < r[1][1] - r[1][0]                               # rank 0 owns fewer vertices
+    assert P.vertex_ranges(V, world) == P.vertex_ranges(V, world, front=0, front_cost=cost)
