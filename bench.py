@@ -145,6 +145,12 @@ def cpu_reference_sample(octaves, iters, budget_s=20.0, division=320, seed=12345
     from oracle import oracle, icosphere
     import numpy as np
     oracle.build()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    oracle.set_num_threads(avail)
     cores = oracle.num_threads()
     pts, cells = icosphere.icosa_sphere(division)
     V = len(pts)

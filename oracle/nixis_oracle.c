@@ -564,6 +564,12 @@ NXO_API void nxo_erode_terrain3(int64_t V, const double *verts, const int32_t *a
     if (!sed_out) free(sed);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must use the host's cores */
+NXO_API void nxo_set_num_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+}
+
 NXO_API int nxo_num_threads(void)
 {
 #ifdef _OPENMP

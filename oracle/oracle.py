@@ -69,6 +69,7 @@ def lib():
         L.nxo_erosion_iteration3.argtypes = [C.c_int64, _f64p, _i32p, _f64p, _f64p, _f64p]
         L.nxo_erode_terrain3.argtypes = [C.c_int64, _f64p, _i32p, _f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.nxo_num_threads.restype = C.c_int
+        L.nxo_set_num_threads.argtypes = [C.c_int]
         if hasattr(L, "nxo_sample_insolation"):
             L.nxo_seasonal_tilt.restype = C.c_double
             L.nxo_seasonal_tilt.argtypes = [C.c_double, C.c_double]
@@ -240,6 +241,11 @@ def height_assembly(height, min_alt=-4000, max_alt=8850, ocean_percent=55.0):
     height -= ocean_level
     height = rescale(height, min_alt, max_alt, mid=0)
     return height, ocean, ocean_level
+
+
+def set_num_threads(n):
+    """Override OMP_NUM_THREADS for the oracle's OpenMP loops (torchrun sets it to 1 in its workers)."""
+    lib().nxo_set_num_threads(int(n))
 
 
 def num_threads():
