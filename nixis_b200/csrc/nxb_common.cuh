@@ -88,6 +88,15 @@ __device__ __forceinline__ void nxb_mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!nxb_mbar_try_wait(bar, parity)) {}
 }
+// the same on a shared-window address computed once (saves the generic -> shared conversion per call)
+__device__ __forceinline__ void nxb_mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    } while (!ok);
+}
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completes on `bar`
 __device__ __forceinline__ void nxb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

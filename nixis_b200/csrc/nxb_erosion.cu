@@ -309,9 +309,14 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         uint32_t ph_full = 0;
         const bool sending = COMM && a.comm.send_ptr != nullptr;
         const int n_early = COMM ? a.comm.n_early : 0;
+        // running shared-window addresses of full[s] / empty[s] and a running stage pointer: the loop
+        // head otherwise re-derives them from s every tile (the sweep is issue-co-limited)
+        const uint32_t full_a0 = nxb_smem_u32(&full[0]), empty_a0 = nxb_smem_u32(&empty[0]);
+        uint32_t full_a = full_a0, empty_a = empty_a0;
+        const EroStage *stp = stage;
         for (int it = 0; it < (int)my_tiles; ++it) {
-            nxb_mbar_wait(&full[s], ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
-            const EroStage &st = stage[s];
+            nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
+            const EroStage &st = *stp;
             const int64_t tile = st.tile;
             const int64_t v = tile * (int64_t)ERO_TILE + c;
             float hn[6], wn[6], d[6];
@@ -369,7 +374,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             }
             }
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nxb_smem_u32(&empty[s])) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
             float hh, ww, ss;
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
             if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
@@ -411,7 +416,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     }
                 }
             }
-            if (++s == n_stages) { s = 0; ph_full ^= 1u; }
+            if (++s == n_stages) { s = 0; ph_full ^= 1u; full_a = full_a0; empty_a = empty_a0; stp = stage; }
+            else { full_a += 8; empty_a += 8; ++stp; }
         }
     }
 #ifdef NXB_ERO_DEBUG_WAIT

@@ -455,6 +455,38 @@ def test_erosion_implicit_adjacency_bit_identical(nx, monkeypatch, k):
     assert k < 700 or plan.n_affine > 0.15 * plan.n_tiles
 
 
+def test_erosion_exchange_capable_kernel_matches_plain_on_one_gpu(nx):
+    """The COMM instantiation of the sweep kernel (the one every multi-GPU rank runs), driven on one
+    GPU with no peers, gives bit for bit what the single-GPU instantiation gives -- with and without
+    an explicit processing order."""
+    import ctypes as C
+    torch = nx.torch
+    from nixis_b200 import _lib
+    rt = nx.rt
+    pipe = nx.pipeline.TerrainPipeline(300, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    h, _, _ = pipe.heights()
+    st = pipe.erosion_state(h.clone())
+    st.run(6)
+    ref = (st.heights.clone(), st.water.clone(), st.sediment.clone())
+    tp = pipe._plan
+    ticket = torch.zeros(4 + 256, dtype=torch.int32, device="cuda")
+    rev = torch.arange(tp.n_tiles - 1, -1, -1, dtype=torch.int32, device="cuda")
+    for order in (None, rev):
+        st2 = pipe.erosion_state(h.clone())
+        src, dst = st2.cur, st2.nxt
+        for _ in range(6):
+            _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st2.dist), None,
+                      rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
+                      tp.n_own, C.c_float(0.3 / 320), None, None, 0, None, None, None, None, None, 0,
+                      C.c_uint32(0), C.c_uint32(0), 0, rt._ptr(ticket), None if order is None else rt._ptr(order), 0, rt._stream())
+            src, dst = dst, src
+        torch.cuda.synchronize()
+        V = pipe.V
+        for a, b in zip(ref, (src[0][:V], src[1][:V], src[2][:V])):
+            assert torch.equal(a, b)
+
+
 def test_config2_d1000_fbm_assembly_erosion_vs_oracle(nx, oracle):
     """BASELINE configs[1..2] scale (d=1000, 10 000 002 vertices): fBm + assembly + 20 sweeps, device
     resident, against the float64 oracle on the same mesh."""
