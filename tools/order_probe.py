@@ -1,4 +1,5 @@
-"""Single-GPU probe: cost of processing tiles out of index order in erode3_plan_kernel."""
+"""Single-GPU probe of the sweep kernel: implicit adjacency on / off, single-GPU vs exchange-capable
+instantiation (run(order) can also time an explicit tile order)."""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -44,16 +45,3 @@ def run_plain(n=50):
 for aff in ("1", "0", "1"):
     os.environ["NXB_ERO_AFFINE"] = aff
     print(f"NXB_ERO_AFFINE={aff}: single-GPU kernel {run_plain():.1f} us, exchange-capable kernel {run(None):.1f} us")
-sys.exit(0)
-print("null order        :", round(run(None), 1), "us")
-print("identity order    :", round(run(ident), 1), "us")
-mask = (torch.arange(n_tiles, device="cuda") % 5 == 0)
-o20 = torch.argsort(mask.to(torch.int8), stable=True).to(torch.int32)
-print("every 5th tile last:", round(run(o20), 1), "us")
-blk = ((torch.arange(n_tiles, device="cuda") // 64) % 5 == 0)
-o20b = torch.argsort(blk.to(torch.int8), stable=True).to(torch.int32)
-print("every 5th 64-block last:", round(run(o20b), 1), "us")
-rev = torch.arange(n_tiles - 1, -1, -1, dtype=torch.int32, device="cuda")
-print("reversed          :", round(run(rev), 1), "us")
-perm = torch.randperm(n_tiles, device="cuda").to(torch.int32)
-print("random permutation:", round(run(perm), 1), "us")
