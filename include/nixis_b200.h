@@ -72,6 +72,15 @@ int nxb_noise4_f32(void *tables, const float *x, const float *y, const float *z,
 int nxb_fbm3_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
                  const double *freq_host, const double *amp_host,
                  const float *init, float *out, float *minmax, void *stream);
+/* The same with the reference's own float64 vertices (device double[n][3], multiplied by `scale`
+ * first: nixis.py:249 `points *= world_radius`; pass 1.0 for radius-scaled vertices).
+ * nr_host[o] = n_freq_o / world_radius (terrain.py:43), amp_host[o] = octave amplitude in output units.
+ * Lattice coordinates, cell and candidate selection are float64 in the reference's operation order, so
+ * the evaluated lattice points are exactly the reference's (ties included); the contributions and
+ * the accumulation are FP32.  nxb_fbm3_f32 is this function on float4 positions promoted to double. */
+int nxb_fbm3_pos64_f32(void *tables, const double *verts, double scale, int64_t n, int n_oct,
+                       const double *nr_host, const double *amp_host,
+                       const float *init, float *out, float *minmax, void *stream);
 /* Reference-exact mode of the same function: IEEE double, no FMA contraction, the reference's
  * operation order -> bit-identical to the numba output for the same float64 vertices.
  * verts: double[n][3] (device), multiplied by `scale` first (nixis.py:249 `points *= world_radius`;
@@ -94,6 +103,15 @@ int nxb_mask_le_f32(const float *h, int64_t n, float level, uint8_t *mask, void 
 int nxb_mesh_icosa_points(int k, int64_t v_begin, int64_t v_end, nxb_float4 *xyz_f32, double *xyz_f64, void *stream);
 /* triangles [t_begin, t_end) as int32[.][3] */
 int nxb_mesh_icosa_cells(int k, int64_t t_begin, int64_t t_end, int32_t *cells, void *stream);
+/* util.py:591-662 build_adjacency + sort_adjacency for rows [v_begin, v_end) of the closed-form icosphere
+ * WITHOUT the cell array or any whole-mesh table (a multi-GPU rank builds only its own rows): the
+ * closed-form triangle generator is scanned, corners inside the range are collected, each vertex
+ * sorts its <= 6 incident triangles by index (= the reference's append order) and walks its ring.
+ * adj_sorted int32[n][6] (global ids, -1 pad), adj_unsorted nullable (the build_adjacency rows);
+ * workspace: nxb_mesh_icosa_adj_rows_workspace(n) bytes (52 B per row).  Synchronous at the end. */
+int64_t nxb_mesh_icosa_adj_rows_workspace(int64_t n_rows);
+int nxb_mesh_icosa_adj_rows(int k, int64_t v_begin, int64_t v_end, int32_t *adj_sorted, int32_t *adj_unsorted,
+                            void *workspace, void *stream);
 /* double[n][3] * scale -> float4 (used to ingest caller-supplied float64 vertices) */
 int nxb_xyz_f64_to_f32(const double *xyz_f64, int64_t n, double scale, nxb_float4 *xyz_f32, void *stream);
 
@@ -180,21 +198,23 @@ int nxb_edge_lengths_f64(const double *nodes /*[.][3]*/, const int32_t *adj, int
 int nxb_mesh_icosa_edge_lengths(int k, const int32_t *adj_rows, int64_t v_begin, int64_t v_end, double radius,
                                 float *dist, void *stream);
 /* Tile plan of the sweep (see csrc/nxb_erosion_plan.cuh): per 256-vertex tile the contiguous halo
- * segments to stage in shared memory and the adjacency re-encoded as 16-bit tile-local codes.
+ * segments to stage in shared memory, the adjacency re-encoded as 16-bit tile-local codes, and the
+ * per-tile constants of the implicit-adjacency kinds.
  * adj: int32[n_own][6] with indices in [0, capacity) (own vertices first, then halo slots of a
  * multi-GPU shard).  capacity = allocated ELEMENTS of every h/w/s buffer later passed to the step
  * (multiple of 256, >= round_up(n_own, 256)).  plan_mem: nxb_erode_plan_bytes(n_own) bytes, 16-byte
- * aligned.  stats_host (nullable) int32[4]: tiles, irregular tiles, max halo slots, affine tiles (implicit
- * adjacency: the sweep reads no adjacency codes for them).  Synchronous. */
+ * aligned.  stats_host (nullable) int32[5]: tiles, irregular tiles, max halo slots, affine tiles
+ * (implicit adjacency: the sweep reads no adjacency codes for them), affine tiles that also qualify
+ * for one stored length per edge.  Synchronous. */
 int64_t nxb_erode_plan_bytes(int64_t n_own);
 int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, void *plan_mem,
                          int32_t *stats_host, void *stream);
 /* One stored length per edge: dist3[v][i] = dist[v][q] of v's i-th larger-numbered neighbour (slot
- * order), float[round_up(n_own,256)][3].  With it the sweep streams 12 B/vertex of edge lengths
- * instead of 24 (48 B per vertex-iteration instead of 60); the plan's code bits say which row holds
- * each slot's length.  Pass dist3 = NULL to the step functions to stream the full table. */
-int64_t nxb_erode_dist3_floats(int64_t n_own);   /* size of the dist3 buffer: the rows plus the tiles' exception rows */
-int nxb_erode_dist3_build(const void *plan_mem, const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream);
+ * order), nxb_erode_dist3_floats(n_own) floats.  With it the sweep streams 12 B/vertex of edge
+ * lengths instead of 24 on the tiles the plan marks (36 B per vertex-iteration instead of 48).
+ * Pass dist3 = NULL to the sweep functions to stream the full table everywhere. */
+int64_t nxb_erode_dist3_floats(int64_t n_own);
+int nxb_erode_dist3_build(const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream);
 /* erosion.py:197-279 erosion_iteration3 for vertices [0, n_own), FP32 state, ping-pong buffers
  * (reads *_in, writes *_out; no copy-back pass).  `rain` is added to every water value read
  * (erosion.py:182-183 `water += rain_amount` fused).  dist: float[round_up(n_own,256)*6]. */
@@ -202,26 +222,30 @@ int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const flo
                              const float *h_in, const float *w_in, const float *s_in,
                              float *h_out, float *w_out, float *s_out,
                              int64_t n_own, float rain, void *stream);
-/* The same sweep fused with the multi-GPU halo exchange in ONE kernel: boundary results are stored
- * straight into the peers' halo slots over NVLink as they are computed, the kernel waits for the
- * peers' flags only before the first tile that reads halo data, and the last CTA raises this rank's
- * flag (flag_value) in every peer.  send_ptr/send_entries: device CSR per tile of {int32 dst,
- * uint16 vertex-in-tile, uint16 peer slot}; peer_h/peer_w/peer_flag: host arrays of NVLink-mapped
- * pointers (peers' OUTPUT buffers of this sweep, their flag slot for this rank); flags: this rank's
- * uint32 flag array; wait_rank: host int32[n_wait]; halo_begin: first halo slot; ticket: device
- * uint32 (zero). */
-int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                                  const float *h_in, const float *w_in, const float *s_in,
-                                  float *h_out, float *w_out, float *s_out,
-                                  int64_t n_own, float rain,
-                                  const int32_t *send_ptr, const void *send_entries, int n_send_peers,
-                                  void *const *peer_h, void *const *peer_w, void *const *peer_flag,
-                                  const void *flags, const int32_t *wait_rank, int n_wait,
-                                  uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
-                                  void *ticket, const int32_t *tile_order /* nullable: processing order */,
-                                  int64_t n_early /* > 0: the first n_early tiles of tile_order are the boundary
-                                  set (send or read halo); flags go up when they are done, not at grid end */,
-                                  void *stream);
+/* erosion.py:180-184: the erode_terrain3 loop, n_sweeps sweeps issued from C (one launch each, chained
+ * with programmatic dependent launch).  Sweep 0 reads buffer set A and writes B, sweep 1 reads B ...:
+ * the result is in A when n_sweeps is even, in B when it is odd. */
+int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
+                       float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                       int64_t n_own, float rain, int64_t n_sweeps, void *stream);
+/* The same loop on one shard of a multi-GPU run, each sweep fused with the halo exchange in ONE
+ * kernel: boundary results are stored straight into the peers' halo slots over NVLink as they are
+ * computed and the last CTA raises this rank's flag in every peer; a one-warp kernel in front of
+ * each sweep waits for the peers' flags of the previous one.  The plan's tile descriptors carry each
+ * tile's range of send_entries (device array of {int32 dst, uint16 vertex-in-tile, uint16 peer slot});
+ * peer_h_a/.. : HOST arrays of n_send_peers NVLink-mapped pointers to the peers' buffer sets A and B
+ * and to their flag slot for this rank; flags: this rank's uint32 flag array; wait_ranks_dev: device
+ * int32[n_wait] source ranks.  Sweep i waits for flag value sweep_base + 1 + i and raises
+ * sweep_base + 2 + i (the halo of the initial state is published with value sweep_base + 1, e.g. by
+ * nxb_halo_put_f32).  ticket: device uint32, zero. */
+int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
+                            float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                            int64_t n_own, float rain, int64_t n_sweeps,
+                            const void *send_entries, int n_send_peers,
+                            void *const *peer_h_a, void *const *peer_w_a,
+                            void *const *peer_h_b, void *const *peer_w_b, void *const *peer_flag,
+                            const void *flags, const int32_t *wait_ranks_dev, int n_wait,
+                            uint32_t sweep_base, void *ticket, void *stream);
 /* Reference-exact mode of the sweep: float64 positions / state, no FMA, the reference's operation and
  * neighbour order -> bit-identical to erosion_iteration3 (erosion.py:197-279) preceded by
  * `water += rain` (erosion.py:182-183).  nodes: double[.][3]; ping-pong buffers of n doubles. */
@@ -247,6 +271,14 @@ int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeers, uint3
 /* the same wait as stream memory operations (cuStreamWaitValue32, one per flag): no kernel, no SM.
  * src_ranks_host: HOST int32[npeers]. */
 int nxb_halo_wait_stream(const void *flags, const int32_t *src_ranks_host, int npeers, uint32_t target, void *stream);
+
+/* Peer-mapped buffers through CUDA IPC (the alternative to torch symmetric memory; also works for two
+ * processes on ONE device): the owner allocates zeroed device memory and exports a 64-byte handle
+ * (HOST buffer), peers open it and receive a device pointer valid in their process.  Synchronous. */
+int nxb_peer_alloc(int64_t bytes, void **ptr_out, void *handle64_host);
+int nxb_peer_open(const void *handle64_host, void **ptr_out);
+int nxb_peer_close(void *ptr);
+int nxb_peer_free(void *ptr);
 
 /* gather / scatter of halo values for the multi-GPU exchange: dst[i] = src[idx[i]] and
  * dst[idx[i]] = src[i] */

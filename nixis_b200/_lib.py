@@ -28,11 +28,14 @@ SIGNATURES = {
     "nxb_noise2_f32": (_i, [_p, _p, _p, _i64, _p, _p]),
     "nxb_noise4_f32": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p]),
     "nxb_fbm3_f32": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "nxb_fbm3_pos64_f32": (_i, [_p, _p, _d, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "nxb_fbm3_f64": (_i, [_p, _p, _i64, _i, _p, _p, _d, _d, _p, _p, _p]),
     "nxb_fbm4_f32": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "nxb_mask_le_f32": (_i, [_p, _i64, _f, _p, _p]),
     "nxb_mesh_icosa_points": (_i, [_i, _i64, _i64, _p, _p, _p]),
     "nxb_mesh_icosa_cells": (_i, [_i, _i64, _i64, _p, _p]),
+    "nxb_mesh_icosa_adj_rows_workspace": (_i64, [_i64]),
+    "nxb_mesh_icosa_adj_rows": (_i, [_i, _i64, _i64, _p, _p, _p, _p]),
     "nxb_xyz_f64_to_f32": (_i, [_p, _i64, _d, _p, _p]),
     "nxb_ll_grid_f64": (_i, [_i, _i, _d, _p, _p]),
     "nxb_ico_nearest3_f64": (_i, [_i, _d, _p, _i64, _p, _p, _p]),
@@ -56,15 +59,20 @@ SIGNATURES = {
     "nxb_erode_plan_bytes": (_i64, [_i64]),
     "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_erode_dist3_floats": (_i64, [_i64]),
-    "nxb_erode_dist3_build": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "nxb_erode_dist3_build": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
-    "nxb_erode3_plan_step_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f,
-                                           _p, _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, C.c_uint32, _i64, _p, _p, _i64, _p]),
+    "nxb_erode3_run_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64, _p]),
+    "nxb_erode3_run_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64,
+                                     _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, C.c_uint32, _p, _p]),
     "nxb_erode3_step_f64": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _d, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "nxb_halo_put_f32": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
     "nxb_halo_wait": (_i, [_p, _p, _i, C.c_uint32, _p]),
     "nxb_halo_wait_stream": (_i, [_p, _p, _i, C.c_uint32, _p]),
+    "nxb_peer_alloc": (_i, [_i64, C.POINTER(_p), _p]),
+    "nxb_peer_open": (_i, [_p, C.POINTER(_p)]),
+    "nxb_peer_close": (_i, [_p]),
+    "nxb_peer_free": (_i, [_p]),
     "nxb_gather_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_scatter_f32": (_i, [_p, _p, _i64, _p, _p]),
     "nxb_f32_to_f64": (_i, [_p, _i64, _p, _p]),
@@ -108,13 +116,15 @@ def check(rc, what=""):
 
 
 # kernels launched per successful call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"nxb_adj_build": 2, "nxb_ffma_peak": 5, "nxb_init_perm": 0, "nxb_tables_create": 0,
-                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0, "nxb_halo_wait_stream": 0, "nxb_erode_dist3_build": 2}
+KERNELS_PER_CALL = {"nxb_adj_build": 2, "nxb_mesh_icosa_adj_rows": 2, "nxb_ffma_peak": 5, "nxb_init_perm": 0, "nxb_tables_create": 0,
+                    "nxb_tables_destroy": 0, "nxb_climate_slice_verts": 0, "nxb_halo_wait_stream": 0,
+                    "nxb_peer_alloc": 0, "nxb_peer_open": 0, "nxb_peer_close": 0, "nxb_peer_free": 0}
 launch_count = 0
 
 
-def call(name, *args):
-    """Call an int-returning entry point and raise on a non-zero status."""
+def call(name, *args, launches=None):
+    """Call an int-returning entry point and raise on a non-zero status.  `launches`: kernels the
+    call launches when that depends on its arguments (the C-side sweep loops)."""
     global launch_count
     check(getattr(load(), name)(*args), name)
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    launch_count += KERNELS_PER_CALL.get(name, 1) if launches is None else launches

@@ -1,39 +1,41 @@
 // Erosion sweeps -- erosion.py:34-40, 76-99, 197-279 -- as a shared-memory-staged stencil.
 //
-// Bound by HBM and by consumer instruction issue at the same time (profiles/r01_ncu_*).
+// Bound by HBM and by consumer instruction issue at the same time (profiles/r01_ncu_*, r02_*).
 // Algorithmic traffic per vertex-iteration of erosion_iteration3:
 //   own h,w,s read 12 B + write 12 B + adjacency row 24 B + own position 12 B = 60 B.
-// What this implementation actually streams per vertex-iteration:
-//   h,w,s read 12 B + write 12 B + 6 edge lengths 24 B = 48 B on affine tiles (implicit adjacency,
-//   ~80 % of the tiles at d = 2500), + 12 B of 16-bit tile-local adjacency on the other tiles.
+// What this implementation streams from HBM per vertex-iteration (nxb_erosion_plan.cuh):
+//   kind 3 (affine tile, one length per edge)  h,w,s read 12 + write 12 + dist3 12       = 36 B
+//   kind 2 (affine tile, full length rows)     ... + 6 edge lengths 24                   = 48 B
+//   kind 1 (explicit codes)                    ... + 24 + 16-bit tile-local adjacency 12 = 60 B
 //
 // History (profiles/r01_ncu_summary.json): v1, one thread per vertex with 18 global gathers
 // (xyz, h, w of 6 neighbours), ran at 45 % of HBM peak with minimal DRAM traffic -- latency bound;
 // v2 streamed the tile's own data with cp.async.bulk but kept the gathers and was then bound by
-// gather latency + instruction issue (322 instr/vertex, six IEEE sqrt sequences, L1 squeezed out by
-// the shared-memory carve-out).  v3 (this file) removes both:
+// gather latency + instruction issue (322 instr/vertex, six IEEE sqrt sequences).  v3 removed both:
 //
 //   * EDGE LENGTHS ARE PRECOMPUTED once, in FP64, and stored as FP32 (erosion.py:227-229 uses the
 //     undisplaced sphere positions, so they never change).  No neighbour positions are read and no
 //     sqrt is evaluated in the sweep; it also removes the cancellation error of differencing FP32
 //     positions (relative 1e-4 at d=2500).
 //   * TILE PLAN (nxb_erosion_plan.cuh): for each tile of 256 consecutive vertices the neighbours
-//     are the tile itself plus <= 8 contiguous index runs (mesh rows above / below, the elements
-//     next to the tile ends).  A producer warp brings the tile's own streams AND those runs of
-//     h / w into shared memory with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an
-//     mbarrier, n_stages tiles ahead; eight consumer warps then read every neighbour value from
-//     shared memory through a 16-bit tile-local adjacency.  No global gathers, no L1 dependence.
-//     The halo runs were just streamed by a neighbouring tile, so they come from L2, not HBM.
-//   * IMPLICIT ADJACENCY (nxb_erosion_plan.cuh, kind 2): tiles whose six neighbour distances are the
-//     same for all 256 vertices are staged as a 264-element window + halo runs and swept without any
-//     adjacency codes: -12 B and -27 instructions per vertex, 0.59 -> 0.51-0.56 ms per sweep at d=2500.
-//   * ONE LENGTH PER EDGE (dist3, nxb_erosion_plan.cuh) is implemented and bit-identical, but OFF by
-//     default: it cuts the DRAM reads from 3.16 GB to 2.53 GB per sweep at d = 2500 (ncu) and still
-//     runs 715-750 us against 590 us, because at 590 us the consumer warps are already issue-bound
-//     (72 % issue-slot utilisation, ~230 instructions per vertex) and decoding which row holds a
-//     slot's length adds ~60 instructions per vertex.  Enable with NXB_ERO_DIST3=1.
+//     are the tile itself plus <= 8 contiguous index runs.  A producer warp brings the tile's own
+//     streams AND those runs of h / w into shared memory with cp.async.bulk (TMA bulk copy, SASS
+//     UBLKCP) completing on an mbarrier, n_stages tiles ahead; eight consumer warps then read every
+//     neighbour value from shared memory.  No global gathers, no L1 dependence.  The halo runs
+//     were just streamed by a neighbouring tile, so they come from L2, not HBM.
+//   * v5 IMPLICIT ADJACENCY (kind 2): no adjacency codes on tiles whose six neighbour distances
+//     are the same for all 256 vertices: 0.59 -> 0.51-0.56 ms per sweep at d=2500.
+//   * v6 (round 2) ONE LENGTH PER EDGE ON AFFINE TILES (kind 3): the round-1 attempt decoded the
+//     owner row per vertex from spare code bits (~50 instructions per vertex, slower than the
+//     bytes it saved); on affine tiles the owner row and entry are per-tile constants, so the
+//     lookup costs nothing.  The explicit-code dist3 variant, the in-kernel flag wait and the
+//     "boundary tiles first" order of round 1 (all measured slower) are gone
+//     from the hot kernel.
 //   * ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
 //     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
+//   * the sweep LOOP lives here (nxb_erode3_run_*): n sweeps are n launches issued from C with
+//     programmatic dependent launch, so the next sweep's CTAs are resident with barriers
+//     initialised and the first descriptor fetched by the time the previous sweep drains.
 #include "nxb_common.cuh"
 #include "nxb_erosion_plan.cuh"
 #include <string.h>
@@ -42,56 +44,44 @@
 #define ERO_STAGES_MAX 4          // pipeline depth is a launch parameter (3: 4 CTAs/SM, 4: 3 CTAs/SM)
 #define ERO_CONSUMER_WARPS (ERO_TILE / 32)
 #define ERO_THREADS (ERO_TILE + 32)
+#define ERO_DIST_FLOATS ((ERO_WIN + ERO_D3_CAP) * 3)
+static_assert(ERO_DIST_FLOATS >= ERO_TILE * 6, "the dist area holds either full rows of the tile or staged dist3 rows");
 
 struct __align__(128) EroStage {
-    float h[ERO_STAGE_ELEMS];           // [own tile | halo segments]
+    float h[ERO_STAGE_ELEMS];           // kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
     float w[ERO_STAGE_ELEMS];
     float s[ERO_TILE];
-    float dist[ERO_TILE * 3 + ERO_D3_CAP * 3];   // kind 1: [256][6] full rows; kind 0: dist3 [own 256 | staged halo slots]
-    uint16_t adj[ERO_TILE * 6];
-    float exc[ERO_EXC * 6];             // kind 0: full rows of the tile's heavy vertices
-    int32_t irregular;
-    int32_t tile;
-    int32_t kind;                       // 0: dist holds dist3 rows, 1: full rows, 2: affine tile (window layout, no codes)
-    int32_t pad0;
-    int32_t affk4[6];                   // kind 2: byte offset of slot q's neighbour relative to &h[c] / &w[c]
-    int32_t pad[30];
+    float dist[ERO_DIST_FLOATS];        // kinds 1/2: [256][6] full rows; kind 3: dist3 rows [window 264 | leading halo slots][3]
+    uint16_t adj[ERO_TILE * 6];         // kind 1 only
+    // header, written by producer lane 0 before it arms the full barrier
+    int32_t kind, irregular, tile, pad0;
+    int32_t send0, send1, pad1, pad2;   // this tile's range of the send-entry list (multi-GPU)
+    int32_t affk4[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &h[c] / &w[c]
+    int32_t d3k4[8];                    // kind 3: byte offset of slot q's edge length relative to &dist[3 c]
 };
 
 #define ERO_MAX_PEERS 8
 
 // One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` of peer slot
-// `peer`'s output buffers.  Entries are grouped by tile (CSR: send_ptr[tile] .. send_ptr[tile+1]).
+// `peer`'s output buffers.  Entries are grouped by tile; the tile's range [send0, send1) sits in its
+// descriptor, so the producer hands it to the consumers with the rest of the stage header (round 1
+// had every consumer thread fetch it with two dependent global loads per tile: +20 % per sweep on
+// a shard).
 struct EroSendEntry { int32_t dst; uint16_t c; uint16_t peer; };
 
 // Fused halo exchange (multi-GPU shards; all pointers null / counts zero on a single GPU):
 //   * consumers store the freshly computed h / w of boundary vertices straight into the peers'
 //     halo slots (NVLink-mapped peer memory) right after computing them;
-//   * the producer warp spins on this rank's flag words only before the first tile that needs halo
-//     data (a segment in the halo area, or an irregular tile);
-//   * the last CTA to finish raises this rank's flag in every peer (after system-scope fences).
+//   * the last CTA to finish raises this rank's flag in every peer (after system-scope fences);
+//   * the peers' flags of the previous sweep are awaited by a one-warp kernel in front of the
+//     sweep (nxb_halo.cu), overlapped with this kernel's prologue by programmatic dependent launch.
 struct EroComm {
-    const int32_t *send_ptr;            // [n_tiles + 1], null = no sends
     const EroSendEntry *send_entries;
     float *peer_h[ERO_MAX_PEERS], *peer_w[ERO_MAX_PEERS];   // peers' OUTPUT buffers of this sweep
     uint32_t *peer_flag[ERO_MAX_PEERS]; // peers' flag slot for this rank
     int n_send_peers;
-    const uint32_t *flags;              // this rank's flag array (written by the peers)
-    int32_t wait_rank[ERO_MAX_PEERS];
-    int n_wait;
-    uint32_t wait_target, flag_value;
-    int64_t halo_begin;                 // first halo slot (n_own_pad)
+    uint32_t flag_value;
     unsigned int *ticket;
-    // processing order of the tiles (null = index order).  The sharded driver puts the tiles that
-    // read halo slots LAST, so by the time a CTA reaches them the peers' flags are already up and
-    // the wait hides behind interior work.
-    const int32_t *tile_order;
-    // > 0: the first n_early tiles of the processing order are the boundary set (every tile that
-    // sends or reads halo slots).  The flags are raised as soon as those tiles are done -- their
-    // boundary values are in the peers' memory and this rank no longer reads its halo slots of this
-    // sweep -- not at the end of the grid, so the flag latency, the peers' launch gap and this rank's
-    // tail hide behind the interior tiles.
-    int n_early;
 };
 
 struct EroPlanArgs {
@@ -99,7 +89,6 @@ struct EroPlanArgs {
     const int32_t *adj;                                 // int32 ELL (irregular tiles only)
     const float *dist;                                  // full table [.][6]
     const float *dist3;                                 // one entry per edge [.][3] (null: full table only)
-    const float *exc;                                   // [n_tiles][ERO_EXC][6] rows of heavy vertices
     int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
     const float *h_in, *w_in, *s_in;
@@ -140,6 +129,11 @@ __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i
     if (ss > cw) { hh += ss - cw; ss -= ss - cw; }
 }
 
+__device__ __forceinline__ float lds_f32_at(const char *base, int byte_off)
+{
+    return *reinterpret_cast<const float *>(base + byte_off);
+}
+
 // COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop
 // (the sweep is issue-co-limited: each instruction per vertex counts).
 template <bool COMM>
@@ -150,7 +144,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     EroStage *stage = reinterpret_cast<EroStage *>(smem_raw);
     __shared__ __align__(8) uint64_t full[ERO_STAGES_MAX], empty[ERO_STAGES_MAX];
     const int n_stages = a.n_stages;
-    __shared__ float send_h[ERO_TILE], send_w[ERO_TILE];
+    __shared__ float send_h[COMM ? ERO_TILE : 1], send_w[COMM ? ERO_TILE : 1];
     __shared__ bool s_last;
     bool cta_sent = false;
 
@@ -158,62 +152,38 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     const int64_t n_tiles = (a.n_own + ERO_TILE - 1) / ERO_TILE;
     const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+    // Programmatic dependent launch: let the next kernel of the stream (the flag wait / the next
+    // sweep) become resident as this grid's CTAs retire; it blocks in its own griddepcontrol.wait
+    // until this grid has completed and flushed.  No-ops when launched without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < ERO_STAGES_MAX; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
         nxb_fence_mbar_init();
     }
+    // the plan is constant: the first descriptor is fetched before the previous sweep has drained
+    const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
+    int32_t word = 0;                           // producer warp: this lane's word of the 32-word descriptor
+    if (warp == 0 && my_tiles > 0) word = __ldg(dw + (int64_t)blockIdx.x * ERO_DESC_WORDS + lane);
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous sweep's output is complete and visible
 
-#ifdef NXB_ERO_DEBUG_WAIT
-    unsigned long long dbg_t0 = 0; long long dbg_c0 = 0;
-    if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-        dbg_c0 = clock64();
-        a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 0] = (unsigned)dbg_t0;
-    }
-#endif
     if (warp == 0) {
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
-        const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
-        int32_t word = 0;                       // this lane's word of the 16-word descriptor
-        bool halo_ready = !COMM || a.comm.n_wait == 0;
-        const int32_t *order = COMM ? a.comm.tile_order : nullptr;
-        // order lookups are batched: lane l holds the entry of iteration 32 b + l, the next batch is
-        // already in flight.  (One dependent __ldg per tile in front of the descriptor load made the
-        // producer latency-bound: +30% per sweep.)  tile_of is called with i = 0, 1, 2, ... in turn.
-        int32_t ord_cur = 0, ord_nxt = 0;
-        auto ord_load = [&](int64_t b) -> int32_t {
-            const int64_t i = b * 32 + lane;
-            return i < my_tiles ? __ldg(order + blockIdx.x + i * gridDim.x) : 0;
-        };
-        if (order) { ord_cur = ord_load(0); ord_nxt = ord_load(1); }
-        auto tile_of = [&](int64_t i) -> int64_t {       // i-th tile of this CTA
-            if (!order) return blockIdx.x + i * gridDim.x;
-            if (i > 0 && (i & 31) == 0) { ord_cur = ord_nxt; ord_nxt = ord_load((i >> 5) + 1); }
-            return (int64_t)__shfl_sync(0xffffffffu, ord_cur, (int)(i & 31));
-        };
-        int64_t tile = my_tiles > 0 ? tile_of(0) : 0;
-        int64_t tile_next = my_tiles > 1 ? tile_of(1) : 0;
-        if (my_tiles > 0) word = __ldg(dw + tile * ERO_DESC_WORDS + lane);
         int s = 0;
         uint32_t ph_empty = 1;                  // parity the empty barrier of stage s must have passed
         for (int it = 0; it < (int)my_tiles; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
             const int64_t v0 = tile * ERO_TILE;
-            const int32_t tile_id = (int32_t)tile;
-            // descriptor words: see ERO_DW_* (seg_start | seg_len pairs | seg_off pairs | nseg | irregular | halo_used | d3 | affine | K_q)
-            const int32_t cur = word;
-            if (it + 1 < my_tiles) word = __ldg(dw + tile_next * ERO_DESC_WORDS + lane);
-            tile = tile_next;
-            if (it + 2 < my_tiles) tile_next = tile_of(it + 2);
+            const int32_t cur = word;           // descriptor words: see ERO_DW_*
+            if (it + 1 < my_tiles) word = __ldg(dw + (tile + gridDim.x) * ERO_DESC_WORDS + lane);
             const int nseg = __shfl_sync(0xffffffffu, cur, ERO_DW_NSEG);
             const int irregular = __shfl_sync(0xffffffffu, cur, ERO_DW_IRREGULAR);
             const int halo_used = __shfl_sync(0xffffffffu, cur, ERO_DW_HALO_USED);
             const int d3word = __shfl_sync(0xffffffffu, cur, ERO_DW_D3);
             const int affine = (a.use_affine && !irregular) ? __shfl_sync(0xffffffffu, cur, ERO_DW_AFFINE) : 0;
-            const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1), kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
-            const int kind = affine ? ERO_KIND_AFFINE : ((a.dist3 == nullptr || irregular) ? 1 : (d3word & 0xff));   // 0: dist3, 1: full rows
-            const uint32_t d3_used = kind == 0 ? (uint32_t)(d3word >> 8) : 0u;
+            const int kind = !affine ? ERO_KIND_CODES : ((a.dist3 != nullptr && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE);
+            const uint32_t d3_rows = kind == ERO_KIND_AFFINE3 ? (uint32_t)(d3word >> 8) : 0u;
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
@@ -221,83 +191,59 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_OFF + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
-            if (!halo_ready) {
-                // does this tile read halo slots?  (a segment in the halo area, or global gathers)
-                // (an affine tile reads the 4 elements after its end through its window, not a run)
-                const bool mine = (q >= 0 && q < nseg && (int64_t)seg_start >= a.comm.halo_begin) || irregular ||
-                                  (affine && v0 + ERO_TILE + ERO_WIN_PAD > a.comm.halo_begin);
-                if (__any_sync(0xffffffffu, mine)) {
-                    if (lane < a.comm.n_wait) {
-                        const volatile uint32_t *f = a.comm.flags + a.comm.wait_rank[lane];
-                        // gentle polling: hundreds of CTAs hammering one L2 line delay the very
-                        // NVLink write they are waiting for
-                        unsigned ns = 64;
-#ifdef NXB_ERO_DEBUG_WAIT
-                        unsigned long long t0, t1;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                        bool spun = false;
-#endif
-                        while ((int32_t)(*f - a.comm.wait_target) < 0) {
-                            __nanosleep(ns); if (ns < 1024) ns *= 2;
-#ifdef NXB_ERO_DEBUG_WAIT
-                            spun = true;
-#endif
-                        }
-#ifdef NXB_ERO_DEBUG_WAIT
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (spun) { atomicAdd(a.comm.ticket + 1, 1u); atomicMax(a.comm.ticket + 2, (unsigned)(t1 - t0)); }
-                        atomicMax(a.comm.ticket + 3, (unsigned)it);
-                        if (blockIdx.x == 0 && lane == 0) a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 1] = (unsigned)t1;
-#endif
-                    }
-                    __threadfence_system();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __syncwarp();
-                    halo_ready = true;
-                }
-            }
+            // header words travel lane -> lane 0: K_q (3 words), dist3 offsets (3 words), send range (2 words)
+            const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
+                      kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
+            const int dk0 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K), dk1 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K + 1),
+                      dk2 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K + 2);
+            const int sd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), sd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
-            if (kind == ERO_KIND_AFFINE) {
+            if (lane == 0) {
+                st.kind = kind; st.irregular = irregular; st.tile = (int32_t)tile;
+                if (COMM) { st.send0 = sd0; st.send1 = sd1; }
+            }
+            if (kind != ERO_KIND_CODES) {
                 // window layout: [v0 - 4, v0 + 260) of h and w, halo runs behind it; no adjacency codes
                 if (lane == 0) {
-                    st.irregular = 0; st.tile = tile_id; st.kind = kind;
                     st.affk4[0] = (int)(int16_t)(kw0 & 0xffff) * 4; st.affk4[1] = (kw0 >> 16) * 4;
                     st.affk4[2] = (int)(int16_t)(kw1 & 0xffff) * 4; st.affk4[3] = (kw1 >> 16) * 4;
                     st.affk4[4] = (int)(int16_t)(kw2 & 0xffff) * 4; st.affk4[5] = (kw2 >> 16) * 4;
-                    nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_WIN * 8 + ERO_TILE * (4 + 24)) + (uint32_t)halo_used * 8u);
+                    uint32_t tx = (uint32_t)(ERO_WIN * 8 + ERO_TILE * 4) + (uint32_t)halo_used * 8u;
+                    if (kind == ERO_KIND_AFFINE3) {
+                        st.d3k4[0] = (int)(int16_t)(dk0 & 0xffff) * 4; st.d3k4[1] = (dk0 >> 16) * 4;
+                        st.d3k4[2] = (int)(int16_t)(dk1 & 0xffff) * 4; st.d3k4[3] = (dk1 >> 16) * 4;
+                        st.d3k4[4] = (int)(int16_t)(dk2 & 0xffff) * 4; st.d3k4[5] = (dk2 >> 16) * 4;
+                        tx += (uint32_t)(ERO_WIN * 12) + d3_rows * 12u;
+                    } else {
+                        tx += (uint32_t)(ERO_TILE * 24);
+                    }
+                    nxb_mbar_expect_tx(&full[s], tx);
                     nxb_bulk_g2s(st.h, a.h_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
                     nxb_bulk_g2s(st.w, a.w_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
                     nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
-                    nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
+                    if (kind == ERO_KIND_AFFINE3) nxb_bulk_g2s(st.dist, a.dist3 + (v0 - ERO_WIN_PAD) * 3, ERO_WIN * 12, &full[s]);
+                    else                          nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 } else if (q < nseg) {
                     nxb_bulk_g2s(st.h + ERO_WIN + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
                     nxb_bulk_g2s(st.w + ERO_WIN + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+                    if (seg_off < d3_rows) {
+                        // dist3 rows of the (smaller-numbered) vertices of this run: owners of the backward edges
+                        const uint32_t n3 = min(seg_len, d3_rows - seg_off);
+                        nxb_bulk_g2s(st.dist + (ERO_WIN + seg_off) * 3, a.dist3 + (int64_t)seg_start * 3, n3 * 12u, &full[s]);
+                    }
                 }
             } else if (lane == 0) {
-                st.irregular = irregular;
-                st.tile = tile_id;
-                st.kind = kind;
                 const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
-                const uint32_t dist_bytes = kind == 0 ? (uint32_t)(ERO_TILE * 12 + ERO_EXC * 24) + d3_used * 12u : (uint32_t)(ERO_TILE * 24);
-                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 12)) + dist_bytes + halo_bytes);
+                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
                 nxb_bulk_g2s(st.h, a.h_in + v0, ERO_TILE * 4, &full[s]);
                 nxb_bulk_g2s(st.w, a.w_in + v0, ERO_TILE * 4, &full[s]);
                 nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
-                if (kind == 0) {
-                    nxb_bulk_g2s(st.dist, a.dist3 + v0 * 3, ERO_TILE * 12, &full[s]);
-                    nxb_bulk_g2s(st.exc, a.exc + (int64_t)tile_id * (ERO_EXC * 6), ERO_EXC * 24, &full[s]);
-                }
-                else           nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
+                nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 nxb_bulk_g2s(st.adj, a.adj16 + v0 * 6, ERO_TILE * 12, &full[s]);
             } else if (q < nseg && !irregular) {
                 nxb_bulk_g2s(st.h + ERO_TILE + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
                 nxb_bulk_g2s(st.w + ERO_TILE + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
-                if (seg_off < d3_used) {
-                    // dist3 rows of the (smaller-numbered) vertices of this run: owners of backward edges
-                    const uint32_t n3 = min(seg_len, d3_used - seg_off);
-                    nxb_bulk_g2s(st.dist + (ERO_TILE + seg_off) * 3, a.dist3 + (int64_t)seg_start * 3, n3 * 12u, &full[s]);
-                }
             }
             __syncwarp();
             if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
@@ -307,8 +253,6 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const int c = tid - 32;
         int s = 0;
         uint32_t ph_full = 0;
-        const bool sending = COMM && a.comm.send_ptr != nullptr;
-        const int n_early = COMM ? a.comm.n_early : 0;
         // running shared-window addresses of full[s] / empty[s] and a running stage pointer: the loop
         // head otherwise re-derives them from s every tile (the sweep is issue-co-limited)
         const uint32_t full_a0 = nxb_smem_u32(&full[0]), empty_a0 = nxb_smem_u32(&empty[0]);
@@ -317,129 +261,86 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         for (int it = 0; it < (int)my_tiles; ++it) {
             nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
             const EroStage &st = *stp;
-            const int64_t tile = st.tile;
-            const int64_t v = tile * (int64_t)ERO_TILE + c;
+            const int kind = st.kind;
+            const int64_t v = (int64_t)st.tile * ERO_TILE + c;
+            int32_t e0 = 0, e1 = 0;
+            if (COMM) { e0 = st.send0; e1 = st.send1; }
             float hn[6], wn[6], d[6];
             float me, wo, so;
-            if (st.kind == ERO_KIND_AFFINE) {
+            if (kind != ERO_KIND_CODES) {
                 // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
                 const char *hb = reinterpret_cast<const char *>(st.h + c), *wb = reinterpret_cast<const char *>(st.w + c);
                 me = st.h[c + ERO_WIN_PAD]; wo = st.w[c + ERO_WIN_PAD]; so = st.s[c];
+                const int4 ka = *reinterpret_cast<const int4 *>(st.affk4);
+                const int2 kb = *reinterpret_cast<const int2 *>(st.affk4 + 4);
+                hn[0] = lds_f32_at(hb, ka.x); wn[0] = lds_f32_at(wb, ka.x);
+                hn[1] = lds_f32_at(hb, ka.y); wn[1] = lds_f32_at(wb, ka.y);
+                hn[2] = lds_f32_at(hb, ka.z); wn[2] = lds_f32_at(wb, ka.z);
+                hn[3] = lds_f32_at(hb, ka.w); wn[3] = lds_f32_at(wb, ka.w);
+                hn[4] = lds_f32_at(hb, kb.x); wn[4] = lds_f32_at(wb, kb.x);
+                hn[5] = lds_f32_at(hb, kb.y); wn[5] = lds_f32_at(wb, kb.y);
+                if (kind == ERO_KIND_AFFINE3) {
+                    // one stored length per edge: own dist3 row (forward slots) or the neighbour's row
+                    // (backward slots), entry and row distance constant over the tile
+                    const char *db = reinterpret_cast<const char *>(st.dist + c * 3);
+                    const int4 da = *reinterpret_cast<const int4 *>(st.d3k4);
+                    const int2 dc = *reinterpret_cast<const int2 *>(st.d3k4 + 4);
+                    d[0] = lds_f32_at(db, da.x); d[1] = lds_f32_at(db, da.y); d[2] = lds_f32_at(db, da.z);
+                    d[3] = lds_f32_at(db, da.w); d[4] = lds_f32_at(db, dc.x); d[5] = lds_f32_at(db, dc.y);
+                } else {
+                    const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
+                    const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
+                    d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+                }
+            } else {
+                me = st.h[c]; wo = st.w[c]; so = st.s[c];
                 const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
                 const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
                 d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+                if (!st.irregular) {
+                    const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
+                    const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
+                    const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int k4 = st.affk4[q];
-                    hn[q] = *reinterpret_cast<const float *>(hb + k4);
-                    wn[q] = *reinterpret_cast<const float *>(wb + k4);
+                    for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q] & ERO_CODE_POS]; wn[q] = st.w[code[q] & ERO_CODE_POS]; }
+                } else {
+                    // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
+                    const int64_t vv = v < a.n_own ? v : a.n_own - 1;
+                    const int2 *rp = reinterpret_cast<const int2 *>(a.adj + vv * 6);
+                    const int2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+                    const int32_t row[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
+                        hn[q] = __ldg(a.h_in + n); wn[q] = __ldg(a.w_in + n);
+                    }
                 }
-            } else {
-            me = st.h[c]; wo = st.w[c]; so = st.s[c];
-            const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
-            const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
-            const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
-            if (st.kind == 0 && !(code[0] & ERO_CODE_HEAVY)) {
-                // one stored length per edge: from this vertex's dist3 row, or from the row of the
-                // (smaller-numbered, staged) neighbour that owns the edge
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const uint32_t row = (code[q] & ERO_CODE_BACK) ? (code[q] & ERO_CODE_POS) : (uint32_t)c;
-                    d[q] = st.dist[row * 3 + ((code[q] >> ERO_CODE_I_SHIFT) & 3u)];
-                }
-            } else if (st.kind == 0) {
-                // skeleton-adjacent vertex: its full row travels with the tile (exception rows)
-                const float *ep = st.exc + ((code[0] >> ERO_CODE_EXC_SHIFT) & 3u) * 6;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) d[q] = ep[q];
-            } else {
-                const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
-                const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
-                d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
-            }
-            if (!st.irregular) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q] & ERO_CODE_POS]; wn[q] = st.w[code[q] & ERO_CODE_POS]; }
-            } else {
-                // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
-                const int64_t vv = v < a.n_own ? v : a.n_own - 1;
-                const int2 *rp = reinterpret_cast<const int2 *>(a.adj + vv * 6);
-                const int2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
-                const int32_t row[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
-                    hn[q] = __ldg(a.h_in + n); wn[q] = __ldg(a.w_in + n);
-                }
-            }
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
             float hh, ww, ss;
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
             if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
-            if (sending) {
-                const int32_t e0 = __ldg(a.comm.send_ptr + tile), e1 = __ldg(a.comm.send_ptr + tile + 1);
-                if (e1 > e0) {                  // uniform over the 8 consumer warps
-                    send_h[c] = hh; send_w[c] = ww;
-                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
-                    for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
-                        const EroSendEntry en = a.comm.send_entries[e];
-                        a.comm.peer_h[en.peer][en.dst] = send_h[en.c];
-                        a.comm.peer_w[en.peer][en.dst] = send_w[en.c];
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
-                    cta_sent = true;
-                }
-            }
-            const int slot = (int)blockIdx.x + it * (int)gridDim.x;
-            if (COMM && slot < n_early && slot + (int)gridDim.x >= n_early) {
-                // this CTA's LAST boundary tile is done: all 8 consumer warps have read their inputs
-                // and stored to the peers.  One system fence per CTA (a fence per tile costs
-                // microseconds each while NVLink stores are in flight), then check in.
+            if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
+                send_h[c] = hh; send_w[c] = ww;
                 asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
-                if (c == 0) {
-                    __threadfence_system();         // cumulative over the CTA's peer stores (barrier above)
-                    const unsigned n_cta = a.comm.n_early < (int)gridDim.x ? (unsigned)a.comm.n_early : gridDim.x;
-                    if (atomicAdd(a.comm.ticket, 1u) == n_cta - 1u) {
-                        *a.comm.ticket = 0;
-                        __threadfence_system();
-                        for (int p = 0; p < a.comm.n_send_peers; ++p) {
-                            volatile uint32_t *f = a.comm.peer_flag[p];
-                            *f = a.comm.flag_value;
-                        }
-                        __threadfence_system();
-#ifdef NXB_ERO_DEBUG_WAIT
-                        { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                          a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
-#endif
-                    }
+                for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
+                    const EroSendEntry en = a.comm.send_entries[e];
+                    a.comm.peer_h[en.peer][en.dst] = send_h[en.c];
+                    a.comm.peer_w[en.peer][en.dst] = send_w[en.c];
                 }
+                asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
+                cta_sent = true;
             }
             if (++s == n_stages) { s = 0; ph_full ^= 1u; full_a = full_a0; empty_a = empty_a0; stp = stage; }
             else { full_a += 8; empty_a += 8; ++stp; }
         }
     }
-#ifdef NXB_ERO_DEBUG_WAIT
-    if (a.comm.ticket && (tid == 0 || tid == 32)) {           // when did this CTA's producer / consumers run dry
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMax(a.comm.ticket + 4 + 8 * (a.comm.flag_value % 32) + (tid == 0 ? 4 : 5), (unsigned)t);
-    }
-    if (blockIdx.x == 0 && tid == 0 && a.comm.ticket) {       // SM clock (MHz) seen by CTA 0 over its lifetime
-        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        long long c1 = clock64();
-        a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 3] = (unsigned)((c1 - dbg_c0) * 1000 / (long long)(t1 - dbg_t0 + 1));
-    }
-#endif
-    if (COMM && a.comm.n_send_peers > 0 && a.comm.n_early == 0) {
+    if (COMM && a.comm.n_send_peers > 0) {
         // every peer store of this CTA is visible system-wide before the CTA checks in; the last
         // CTA of the grid then raises this rank's flag in every peer
         if (cta_sent) __threadfence_system();
         __syncthreads();
-#ifdef NXB_ERO_DEBUG_WAIT
-        if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                        atomicMax(a.comm.ticket + 4 + 8 * (a.comm.flag_value % 32) + 6, (unsigned)t); }
-#endif
         if (tid == 0) s_last = (atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1);
         __syncthreads();
         if (s_last) {
@@ -450,10 +351,6 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 __threadfence_system();
             }
             if (tid == 0) *a.comm.ticket = 0;
-#ifdef NXB_ERO_DEBUG_WAIT
-            if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                            a.comm.ticket[4 + 8 * (a.comm.flag_value % 32) + 2] = (unsigned)t; }
-#endif
         }
     }
 }
@@ -475,7 +372,7 @@ __device__ __forceinline__ int block_reduce_min(int v, int *scratch)
 
 __global__ void __launch_bounds__(ERO_TILE)
 ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity,
-                EroTileDesc *__restrict__ desc, uint16_t *__restrict__ adj16, int32_t *__restrict__ stats, int want_d3)
+                EroTileDesc *__restrict__ desc, uint16_t *__restrict__ adj16, int32_t *__restrict__ stats)
 {
     __shared__ int scratch[ERO_TILE / 32];
     const int64_t tile = blockIdx.x, v0 = tile * ERO_TILE;
@@ -493,8 +390,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         else { code[q] = 0; open[q] = true; }
     }
     EroTileDesc d;
-    for (int k = 0; k < ERO_NSEG; ++k) { d.seg_start[k] = 0; d.seg_len[k] = 0; d.seg_off[k] = 0; }
-    d.nseg = 0; d.irregular = 0; d.halo_used = 0; d.d3 = 0;
+    memset(&d, 0, sizeof d);
     const int BIG = 0x7fffffff;
     for (int k = 0; k <= ERO_NSEG; ++k) {
         int m = BIG;
@@ -539,55 +435,11 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         d.halo_used += len;
         d.nseg = k + 1;
     }
-    // ---- where each slot's edge length lives (dist3, see nxb_erosion_plan.cuh) ----
-    int d3_need = 0;                    // staged dist3 halo slots this vertex needs (0 = none)
-    bool is_heavy = false;
-    if (!d.irregular && want_d3) {      // 36 scattered reads per vertex: only when the dist3 sweep is asked for
-        bool heavy = false;
-        int fcnt = 0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            if (nb[q] < 0) continue;
-            if ((int64_t)nb[q] > v) { code[q] |= (uint32_t)(fcnt & 3) << ERO_CODE_I_SHIFT; ++fcnt; }
-            else {
-                // the neighbour n owns the edge: entry = rank of v among n's forward neighbours
-                const int64_t n = nb[q];
-                int fn = 0, idx = -1;
-                for (int t = 0; t < 6; ++t) {
-                    const int32_t m = adj[n * 6 + t];
-                    if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
-                }
-                if (fn > 3 || idx < 0) heavy = true;
-                else {
-                    code[q] |= ERO_CODE_BACK | (uint32_t)idx << ERO_CODE_I_SHIFT;
-                    const int pos = (int)(code[q] & ERO_CODE_POS);
-                    if (pos >= ERO_TILE) d3_need = max(d3_need, pos - ERO_TILE + 1);
-                }
-            }
-        }
-        if (fcnt > 3) heavy = true;
-        is_heavy = heavy;
-        if (heavy) d3_need = 0;
-    }
-    // exception row of a heavy vertex = number of heavy vertices before it in the tile
-    {
-        const unsigned bal = __ballot_sync(0xffffffffu, is_heavy);
-        __shared__ int wcount[ERO_TILE / 32];
-        if ((c & 31) == 0) wcount[c >> 5] = __popc(bal);
-        __syncthreads();
-        int before = __popc(bal & ((1u << (c & 31)) - 1u)), total = 0;
-        for (int w = 0; w < ERO_TILE / 32; ++w) { if (w < (c >> 5)) before += wcount[w]; total += wcount[w]; }
-        __syncthreads();
-        if (is_heavy) code[0] |= ERO_CODE_HEAVY | (uint32_t)(before & 3) << ERO_CODE_EXC_SHIFT;
-        if (total > ERO_EXC) d3_need = ERO_D3_CAP + 4;      // too many: the tile streams the full table
-    }
-    d3_need = -block_reduce_min(-d3_need, scratch);
-    d3_need = (d3_need + 3) & ~3;
-    d.d3 = (!want_d3 || d3_need > ERO_D3_CAP) ? 1 : (d3_need << 8);
     // ---- implicit adjacency: is the staging index of every slot's neighbour c + K_q for all c? ----
+    __shared__ int k0[6];
+    int kq[6];
+    int all_ok;
     {
-        __shared__ int k0[6];
-        int kq[6];
         bool ok = !d.irregular && v < n_own && v0 >= ERO_WIN_PAD && v0 + ERO_TILE + ERO_WIN_PAD <= capacity &&
                   ERO_WIN + d.halo_used <= ERO_STAGE_ELEMS;
 #pragma unroll
@@ -603,23 +455,69 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 6; ++q) ok = ok && kq[q] == k0[q];
-        const int all_ok = __syncthreads_and(ok ? 1 : 0);
+        all_ok = __syncthreads_and(ok ? 1 : 0);
         d.affine = all_ok;
         for (int q = 0; q < 6; ++q) d.aff_k[q] = (int16_t)(all_ok ? k0[q] : 0);
-        for (int t = 0; t < 8; ++t) d.pad[t] = 0;
+    }
+    // ---- one length per edge (kind 3): where does slot q's length live in the staged dist3 rows? ----
+    //   forward slot (neighbour index > v): own row, window index c + 4, entry = rank among v's forward slots
+    //   backward slot: the neighbour's row, staging index c + K_q, entry = rank of v among ITS forward slots
+    // The tile qualifies when row distance and entry are the same for all 256 vertices, nobody has
+    // more than 3 forward neighbours, and the backward rows lie in the window or the leading
+    // ERO_D3_CAP halo slots.
+    {
+        __shared__ int j0[6];
+        int jq[6];
+        bool ok3 = all_ok != 0;
+        int d3_need = 0, fcnt = 0;
+        if (ok3) {                          // (36 scattered reads per vertex, affine tiles only)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int64_t n = nb[q];
+                if (n > v) { jq[q] = ERO_WIN_PAD * 3 + fcnt; ++fcnt; }
+                else {
+                    int fn = 0, idx = -1;
+                    for (int t = 0; t < 6; ++t) {
+                        const int32_t m = adj[n * 6 + t];
+                        if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
+                    }
+                    if (fn > 3 || idx < 0) ok3 = false;
+                    jq[q] = kq[q] * 3 + (idx < 0 ? 0 : idx);
+                    const int pos = c + kq[q];              // staging index of the owner row
+                    if (pos < 0) ok3 = false;
+                    if (pos >= ERO_WIN) d3_need = max(d3_need, pos - ERO_WIN + 1);
+                }
+            }
+            if (fcnt > 3) ok3 = false;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) jq[q] = 0;
+        }
+        if (c == 0) for (int q = 0; q < 6; ++q) j0[q] = jq[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ok3 = ok3 && jq[q] == j0[q] && jq[q] >= 0 && jq[q] < 32768;
+        d3_need = -block_reduce_min(-d3_need, scratch);
+        d3_need = (d3_need + 3) & ~3;
+        if (d3_need > ERO_D3_CAP || d3_need > d.halo_used) ok3 = false;
+        const int all3 = __syncthreads_and(ok3 ? 1 : 0);
+        d.d3 = all3 ? (1 | (d3_need << 8)) : 0;
+        for (int q = 0; q < 6; ++q) d.d3_k[q] = (int16_t)(all3 ? j0[q] : 0);
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles
     if (c == 0) {
         desc[tile] = d;
-        if (d.affine) atomicAdd(stats + 2, 1);
         if (d.irregular) atomicAdd(stats, 1);
         atomicMax(stats + 1, d.halo_used);
+        if (d.affine) atomicAdd(stats + 2, 1);
+        if (d.d3 & 1) atomicAdd(stats + 3, 1);
     }
 }
 
 // dist3[v][i] = length of the edge to v's i-th larger-numbered neighbour in slot order (rows with
-// more than 3 such neighbours -- the mesh skeleton -- are never referenced: see the plan's heavy bit)
+// more than 3 such neighbours -- the mesh skeleton, shard seams -- are never referenced: their tiles
+// are not kind 3)
 __global__ void __launch_bounds__(256)
 dist3_build_kernel(const int32_t *__restrict__ adj, const float *__restrict__ dist, int64_t n_own, int64_t n_rows,
                    float *__restrict__ dist3)
@@ -638,40 +536,21 @@ dist3_build_kernel(const int32_t *__restrict__ adj, const float *__restrict__ di
     }
 }
 
-// exception rows: the full 6 lengths of every heavy vertex, at [tile][row from the vertex's code]
-__global__ void __launch_bounds__(256)
-exc_build_kernel(const uint16_t *__restrict__ adj16, const float *__restrict__ dist, int64_t n_own, float *__restrict__ exc)
-{
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_own; v += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t c0 = adj16[v * 6];
-        if (c0 & ERO_CODE_HEAVY) {
-            float *row = exc + (v / ERO_TILE) * (ERO_EXC * 6) + ((c0 >> ERO_CODE_EXC_SHIFT) & 3u) * 6;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) row[q] = dist[v * 6 + q];
-        }
-    }
-}
-
+// rows of the dist3 table: the padded own range plus one tile (the last affine tile's window reads 4 rows past it)
 NXB_API int64_t nxb_erode_dist3_floats(int64_t n_own)
 {
     const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
-    return n_tiles * ERO_TILE * 3 + n_tiles * ERO_EXC * 6;
+    return (n_tiles + 1) * ERO_TILE * 3;
 }
 
-NXB_API int nxb_erode_dist3_build(const void *plan_mem, const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream)
+NXB_API int nxb_erode_dist3_build(const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream)
 {
     NXB_ARG(n_own >= 0);
     if (n_own == 0) return NXB_OK;
-    NXB_ARG(plan_mem && adj && dist && dist3 && (((uintptr_t)dist3) & 15) == 0);
-    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE, n_rows = n_tiles * ERO_TILE;
-    const uint16_t *adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
-    float *exc = dist3 + n_rows * 3;
-    NXB_CUDA(cudaMemsetAsync(exc, 0, sizeof(float) * n_tiles * ERO_EXC * 6, (cudaStream_t)stream));
+    NXB_ARG(adj && dist && dist3 && (((uintptr_t)dist3) & 15) == 0);
+    const int64_t n_rows = nxb_erode_dist3_floats(n_own) / 3;
     dist3_build_kernel<<<nxb_grid_resident(dist3_build_kernel, 256, 0, (n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         adj, dist, n_own, n_rows, dist3);
-    NXB_LAUNCH_CHECK();
-    exc_build_kernel<<<nxb_grid_resident(exc_build_kernel, 256, 0, (n_own + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        adj16, dist, n_own, exc);
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
@@ -693,66 +572,119 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
     EroTileDesc *desc = (EroTileDesc *)plan_mem;
     uint16_t *adj16 = (uint16_t *)((char *)plan_mem + n_tiles * sizeof(EroTileDesc));
     int32_t *stats = nullptr;
-    NXB_CUDA(cudaMalloc(&stats, 12));
-    NXB_CUDA(cudaMemsetAsync(stats, 0, 12, st));
-    const char *d3env = getenv("NXB_ERO_DIST3");
-    ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats, d3env && atoi(d3env) == 1);
+    NXB_CUDA(cudaMalloc(&stats, 16));
+    NXB_CUDA(cudaMemsetAsync(stats, 0, 16, st));
+    ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats);
     NXB_LAUNCH_CHECK();
-    int32_t h[3] = {0, 0, 0};
-    NXB_CUDA(cudaMemcpyAsync(h, stats, 12, cudaMemcpyDeviceToHost, st));
+    int32_t h[4] = {0, 0, 0, 0};
+    NXB_CUDA(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, st));
     NXB_CUDA(cudaStreamSynchronize(st));
     NXB_CUDA(cudaFree(stats));
-    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; stats_host[3] = h[2]; }
+    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; stats_host[3] = h[2]; stats_host[4] = h[3]; }
     return NXB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Launch side.  The configuration (pipeline depth, grid, environment switches) is resolved once
+// per call, the sweep loop runs here, not in Python.
+struct EroLaunchCfg {
+    int stages, use_affine, use_dist3, pdl;
+    size_t smem;
+    int grid[2];                // [COMM]
+};
+
 static bool g_ero_attr_set[64] = {false};
 
-static int erode3_plan_launch(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                              const float *h_in, const float *w_in, const float *s_in,
-                              float *h_out, float *w_out, float *s_out,
-                              int64_t n_own, float rain, const EroComm &comm, void *stream)
+static int env_int(const char *name, int dflt)
 {
-    NXB_ARG(n_own >= 0);
-    if (n_own == 0) return NXB_OK;
-    NXB_ARG(plan_mem && adj && dist && h_in && w_in && s_in && h_out && w_out && s_out);
-    NXB_ARG(h_in != h_out && w_in != w_out && s_in != s_out);
-    NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)dist3 | (uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
-    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
-    EroPlanArgs a;
-    a.desc = (const EroTileDesc *)plan_mem;
-    a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
-    a.adj = adj; a.dist = dist; a.dist3 = dist3;
-    a.exc = dist3 ? dist3 + n_tiles * ERO_TILE * 3 : nullptr;
-    a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
-    a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
-    a.n_own = n_own; a.rain = rain;
-    a.comm = comm;
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int ero_launch_cfg(int64_t n_own, EroLaunchCfg &cfg)
+{
+    cfg.stages = env_int("NXB_ERO_STAGES", 3);
+    if (cfg.stages < 2 || cfg.stages > ERO_STAGES_MAX) cfg.stages = 3;
+    cfg.use_affine = env_int("NXB_ERO_AFFINE", 1);          // read per call: tests toggle it
+    cfg.use_dist3 = env_int("NXB_ERO_DIST3", 1);
+    cfg.pdl = env_int("NXB_ERO_PDL", 1);
+    cfg.smem = sizeof(EroStage) * cfg.stages;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
-    static int cfg_stages = 0;
-    if (cfg_stages == 0) {
-        const char *e = getenv("NXB_ERO_STAGES");
-        cfg_stages = e ? atoi(e) : 3;
-        if (cfg_stages < 2 || cfg_stages > ERO_STAGES_MAX) cfg_stages = 3;
-    }
-    a.n_stages = cfg_stages;
-    { const char *e = getenv("NXB_ERO_AFFINE"); a.use_affine = e ? atoi(e) : 1; }      // read per launch: tests toggle it
-    const size_t smem = sizeof(EroStage) * cfg_stages;
     if (dev < 64 && !g_ero_attr_set[dev]) {
-        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int max_smem = (int)(sizeof(EroStage) * ERO_STAGES_MAX);
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         g_ero_attr_set[dev] = true;
     }
-    const bool use_comm = comm.n_send_peers > 0 || comm.n_wait > 0 || comm.tile_order != nullptr || comm.ticket != nullptr;
-    if (use_comm) {
-        int grid = nxb_grid_resident(erode3_plan_kernel<true>, ERO_THREADS, smem, n_tiles);
-        erode3_plan_kernel<true><<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
-    } else {
-        int grid = nxb_grid_resident(erode3_plan_kernel<false>, ERO_THREADS, smem, n_tiles);
-        erode3_plan_kernel<false><<<grid, ERO_THREADS, smem, (cudaStream_t)stream>>>(a);
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    cfg.grid[0] = nxb_grid_resident(erode3_plan_kernel<false>, ERO_THREADS, cfg.smem, n_tiles);
+    cfg.grid[1] = nxb_grid_resident(erode3_plan_kernel<true>, ERO_THREADS, cfg.smem, n_tiles);
+    return NXB_OK;
+}
+
+template <bool COMM>
+static int ero_launch(const EroLaunchCfg &cfg, const EroPlanArgs &a, cudaStream_t st)
+{
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)cfg.grid[COMM ? 1 : 0]);
+    lc.blockDim = dim3(ERO_THREADS);
+    lc.dynamicSmemBytes = cfg.smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = cfg.pdl ? 1 : 0;
+    NXB_CUDA(cudaLaunchKernelEx(&lc, erode3_plan_kernel<COMM>, a));
+    return NXB_OK;
+}
+
+static int ero_base_args(EroPlanArgs &a, const EroLaunchCfg &cfg, const void *plan_mem, const int32_t *adj,
+                         const float *dist, const float *dist3, int64_t n_own, float rain)
+{
+    NXB_ARG(plan_mem && adj && dist);
+    NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)dist3) & 15) == 0);
+    const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    memset(&a, 0, sizeof a);
+    a.desc = (const EroTileDesc *)plan_mem;
+    a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
+    a.adj = adj; a.dist = dist; a.dist3 = cfg.use_dist3 ? dist3 : nullptr;
+    a.n_own = n_own; a.rain = rain;
+    a.n_stages = cfg.stages; a.use_affine = cfg.use_affine;
+    return NXB_OK;
+}
+
+static int ero_set_buffers(EroPlanArgs &a, const float *h_in, const float *w_in, const float *s_in,
+                           float *h_out, float *w_out, float *s_out)
+{
+    NXB_ARG(h_in && w_in && s_in && h_out && w_out && s_out);
+    NXB_ARG(h_in != h_out && w_in != w_out && s_in != s_out);
+    NXB_ARG((((uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
+    a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
+    a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
+    return NXB_OK;
+}
+
+// n_sweeps sweeps, ping-pong between buffer sets A and B (sweep 0 reads A): the result is in A when
+// n_sweeps is even, in B when it is odd.
+NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
+                               float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                               int64_t n_own, float rain, int64_t n_sweeps, void *stream)
+{
+    NXB_ARG(n_own >= 0 && n_sweeps >= 0);
+    if (n_own == 0 || n_sweeps == 0) return NXB_OK;
+    EroLaunchCfg cfg;
+    int rc = ero_launch_cfg(n_own, cfg);
+    if (rc) return rc;
+    EroPlanArgs a;
+    if ((rc = ero_base_args(a, cfg, plan_mem, adj, dist, dist3, n_own, rain))) return rc;
+    for (int64_t i = 0; i < n_sweeps; ++i) {
+        rc = (i & 1) ? ero_set_buffers(a, h_b, w_b, s_b, h_a, w_a, s_a) : ero_set_buffers(a, h_a, w_a, s_a, h_b, w_b, s_b);
+        if (rc) return rc;
+        if ((rc = ero_launch<false>(cfg, a, (cudaStream_t)stream))) return rc;
     }
-    NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
 
@@ -761,48 +693,56 @@ NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, c
                                      float *h_out, float *w_out, float *s_out,
                                      int64_t n_own, float rain, void *stream)
 {
-    EroComm comm;
-    memset(&comm, 0, sizeof comm);
-    return erode3_plan_launch(plan_mem, adj, dist, dist3, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
+    return nxb_erode3_run_f32(plan_mem, adj, dist, dist3, (float *)h_in, (float *)w_in, (float *)s_in,
+                              h_out, w_out, s_out, n_own, rain, 1, stream);
 }
 
-// Sweep + halo exchange in ONE kernel (see EroComm).  send_ptr / send_entries: device CSR of
-// {int32 dst, uint16 vertex-in-tile, uint16 peer slot}; peer_h / peer_w / peer_flag: host arrays of
-// n_send_peers NVLink-mapped pointers (the peers' OUTPUT buffers of this sweep and their flag slot
-// for this rank); flags: this rank's flag array; wait_rank: host int32[n_wait] source ranks whose
-// flag must reach wait_target before halo slots are read; flag_value: raised in the peers when the
-// whole grid has finished; halo_begin: first halo slot; ticket: device uint32, zero.
-NXB_API int nxb_erode3_plan_step_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                                          const float *h_in, const float *w_in, const float *s_in,
-                                          float *h_out, float *w_out, float *s_out,
-                                          int64_t n_own, float rain,
-                                          const int32_t *send_ptr, const void *send_entries, int n_send_peers,
-                                          void *const *peer_h, void *const *peer_w, void *const *peer_flag,
-                                          const void *flags, const int32_t *wait_rank, int n_wait,
-                                          uint32_t wait_target, uint32_t flag_value, int64_t halo_begin,
-                                          void *ticket, const int32_t *tile_order, int64_t n_early, void *stream)
+int nxb_halo_wait_launch(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, int pdl, cudaStream_t st);
+
+// The sharded sweep loop: per sweep a one-warp wait for the peers' flags of the previous sweep, then
+// the sweep fused with the halo exchange (EroComm).  Sweep i (0-based) reads buffer set A when i is
+// even; it stores boundary results into the peers' OTHER set (peer_h_b / peer_w_b when i is even),
+// waits for flag value sweep_base + 1 + i and raises sweep_base + 2 + i.
+NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
+                                    float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                                    int64_t n_own, float rain, int64_t n_sweeps,
+                                    const void *send_entries, int n_send_peers,
+                                    void *const *peer_h_a, void *const *peer_w_a,
+                                    void *const *peer_h_b, void *const *peer_w_b, void *const *peer_flag,
+                                    const void *flags, const int32_t *wait_ranks_dev, int n_wait,
+                                    uint32_t sweep_base, void *ticket, void *stream)
 {
-    NXB_ARG(n_early >= 0 && n_early < (1ll << 31) && (n_early == 0 || (tile_order && n_send_peers > 0)));
-    NXB_ARG(n_send_peers >= 0 && n_send_peers <= ERO_MAX_PEERS && n_wait >= 0 && n_wait <= ERO_MAX_PEERS);
-    NXB_ARG(n_send_peers == 0 || (send_ptr && send_entries && peer_h && peer_w && peer_flag && ticket));
-    NXB_ARG(n_wait == 0 || (flags && wait_rank));
-    EroComm comm;
-    memset(&comm, 0, sizeof comm);
-    if (n_send_peers > 0) {
-        comm.send_ptr = send_ptr; comm.send_entries = (const EroSendEntry *)send_entries;
-        for (int p = 0; p < n_send_peers; ++p) {
-            comm.peer_h[p] = (float *)peer_h[p]; comm.peer_w[p] = (float *)peer_w[p]; comm.peer_flag[p] = (uint32_t *)peer_flag[p];
+    NXB_ARG(n_own >= 0 && n_sweeps >= 0);
+    NXB_ARG(n_send_peers >= 0 && n_send_peers <= ERO_MAX_PEERS && n_wait >= 0 && n_wait <= 32);
+    NXB_ARG(n_send_peers == 0 || (send_entries && peer_h_a && peer_w_a && peer_h_b && peer_w_b && peer_flag && ticket));
+    NXB_ARG(n_wait == 0 || (flags && wait_ranks_dev));
+    if (n_sweeps == 0) return NXB_OK;
+    EroLaunchCfg cfg;
+    int rc = ero_launch_cfg(n_own, cfg);
+    if (rc) return rc;
+    EroPlanArgs a;
+    if (n_own > 0 && (rc = ero_base_args(a, cfg, plan_mem, adj, dist, dist3, n_own, rain))) return rc;
+    for (int64_t i = 0; i < n_sweeps; ++i) {
+        if (n_wait > 0 && (rc = nxb_halo_wait_launch(flags, wait_ranks_dev, n_wait, sweep_base + 1u + (uint32_t)i, cfg.pdl, (cudaStream_t)stream))) return rc;
+        if (n_own == 0) continue;
+        const bool odd = (i & 1) != 0;
+        rc = odd ? ero_set_buffers(a, h_b, w_b, s_b, h_a, w_a, s_a) : ero_set_buffers(a, h_a, w_a, s_a, h_b, w_b, s_b);
+        if (rc) return rc;
+        memset(&a.comm, 0, sizeof a.comm);
+        if (n_send_peers > 0) {
+            a.comm.send_entries = (const EroSendEntry *)send_entries;
+            for (int p = 0; p < n_send_peers; ++p) {
+                a.comm.peer_h[p] = (float *)(odd ? peer_h_a[p] : peer_h_b[p]);
+                a.comm.peer_w[p] = (float *)(odd ? peer_w_a[p] : peer_w_b[p]);
+                a.comm.peer_flag[p] = (uint32_t *)peer_flag[p];
+            }
+            a.comm.n_send_peers = n_send_peers;
+            a.comm.ticket = (unsigned int *)ticket;
+            a.comm.flag_value = sweep_base + 2u + (uint32_t)i;
         }
-        comm.n_send_peers = n_send_peers;
-        comm.ticket = (unsigned int *)ticket;
+        if ((rc = ero_launch<true>(cfg, a, (cudaStream_t)stream))) return rc;
     }
-    comm.flags = (const uint32_t *)flags;
-    for (int p = 0; p < n_wait; ++p) comm.wait_rank[p] = wait_rank[p];
-    comm.n_wait = n_wait;
-    comm.wait_target = wait_target; comm.flag_value = flag_value; comm.halo_begin = halo_begin;
-    comm.tile_order = tile_order;
-    comm.n_early = (int)n_early;
-    return erode3_plan_launch(plan_mem, adj, dist, dist3, h_in, w_in, s_in, h_out, w_out, s_out, n_own, rain, comm, stream);
+    return NXB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

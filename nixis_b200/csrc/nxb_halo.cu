@@ -12,6 +12,7 @@
 // Message sizes are 10^4..10^5 vertices x 8 B per peer: latency, not bandwidth, is what matters,
 // which is why this avoids per-peer launches (one fused kernel for all peers).
 #include "nxb_common.cuh"
+#include <string.h>
 
 #define HALO_MAX_PEERS 8
 
@@ -93,12 +94,32 @@ NXB_API int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send
 
 __global__ void halo_wait_kernel(const uint32_t *flags, const int32_t *src_ranks, int npeers, uint32_t target)
 {
+    // programmatic dependent launch (no-ops without the launch attribute): the sweep behind this
+    // kernel may become resident now; this kernel itself may have started before the previous
+    // sweep drained, so it must not EXIT before that sweep is complete (griddepcontrol.wait) --
+    // the next sweep's own griddepcontrol.wait only covers this kernel.
+    asm volatile("griddepcontrol.launch_dependents;");
     if ((int)threadIdx.x < npeers) {
         const volatile uint32_t *f = flags + src_ranks[threadIdx.x];
         // flags only grow; wrap-safe comparison
         while ((int32_t)(*f - target) < 0) { __nanosleep(20); }
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence_system();
+}
+
+int nxb_halo_wait_launch(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, int pdl, cudaStream_t st)
+{
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(1); lc.blockDim = dim3(32); lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = pdl ? 1 : 0;
+    NXB_CUDA(cudaLaunchKernelEx(&lc, halo_wait_kernel, (const uint32_t *)flags, src_ranks, npeers, target));
+    return NXB_OK;
 }
 
 // flags: this rank's flag array (one uint32 per source rank); src_ranks: device int32[npeers]
@@ -107,9 +128,7 @@ NXB_API int nxb_halo_wait(const void *flags, const int32_t *src_ranks, int npeer
     NXB_ARG(npeers >= 0 && npeers <= 32);
     if (npeers == 0) return NXB_OK;
     NXB_ARG(flags && src_ranks);
-    halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const uint32_t *)flags, src_ranks, npeers, target);
-    NXB_LAUNCH_CHECK();
-    return NXB_OK;
+    return nxb_halo_wait_launch(flags, src_ranks, npeers, target, 0, (cudaStream_t)stream);
 }
 
 // The same wait without a kernel: one stream memory operation per source flag
@@ -145,5 +164,49 @@ NXB_API int nxb_halo_wait_stream(const void *flags, const int32_t *src_ranks_hos
         const CUresult r = fn((CUstream)stream, a, target, CU_STREAM_WAIT_VALUE_GEQ);
         if (r != CUDA_SUCCESS) { nxb_set_error("cuStreamWaitValue32 -> CUresult %d", (int)r); return NXB_ERR_CUDA; }
     }
+    return NXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-mapped state buffers without torch symmetric memory: plain cudaMalloc + CUDA IPC handles.
+// The owner allocates and exports a 64-byte handle (exchanged by the host through the process
+// group); every peer process opens it and gets an address it can store to from its kernels --
+// over NVLink between two GPUs, through local memory when both processes share ONE device (which is
+// how tests exercise the peer stores, flags and waits of the fused exchange on a single-GPU box).
+NXB_API int nxb_peer_alloc(int64_t bytes, void **ptr_out, void *handle64_host)
+{
+    NXB_ARG(bytes > 0 && ptr_out && handle64_host);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *p = nullptr;
+    NXB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    NXB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); nxb_set_error("cudaIpcGetMemHandle -> %s", cudaGetErrorString(e)); return NXB_ERR_CUDA; }
+    memcpy(handle64_host, &h, 64);
+    *ptr_out = p;
+    return NXB_OK;
+}
+
+NXB_API int nxb_peer_open(const void *handle64_host, void **ptr_out)
+{
+    NXB_ARG(handle64_host && ptr_out);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void *p = nullptr;
+    NXB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+    return NXB_OK;
+}
+
+NXB_API int nxb_peer_close(void *ptr)
+{
+    if (ptr) NXB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return NXB_OK;
+}
+
+NXB_API int nxb_peer_free(void *ptr)
+{
+    if (ptr) NXB_CUDA(cudaFree(ptr));
     return NXB_OK;
 }

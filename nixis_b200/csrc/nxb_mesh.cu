@@ -163,32 +163,187 @@ __device__ __forceinline__ int32_t face_node(int64_t n, int f, int64_t r, int64_
     return (int32_t)(base + interior_before_row(n, r) + (c - 1));
 }
 
+// triangle t of the k-division icosphere (meshzoo cell order) -> its three global vertex ids
+__device__ __forceinline__ void icosa_cell(int64_t n, int64_t t, int32_t &a, int32_t &b, int32_t &c)
+{
+    const int64_t nn = n * n;
+    int f = (int)(t / nn);
+    int64_t l = t % nn;
+    // triangles before row i: 2*n*i - i*i ; row i = largest with that <= l
+    int64_t i = (int64_t)((double)n - sqrt((double)(nn - l)));
+    if (i < 0) i = 0;
+    if (i > n - 1) i = n - 1;
+    while (i > 0 && 2 * n * i - i * i > l) --i;
+    while (i < n - 1 && 2 * n * (i + 1) - (i + 1) * (i + 1) <= l) ++i;
+    int64_t r = l - (2 * n * i - i * i);
+    if (r < n - i) {                 // up: (i,j) (i,j+1) (i+1,j)
+        int64_t j = r;
+        a = face_node(n, f, i, j); b = face_node(n, f, i, j + 1); c = face_node(n, f, i + 1, j);
+    } else {                         // down: (i,j+1) (i+1,j+1) (i+1,j)
+        int64_t j = r - (n - i);
+        a = face_node(n, f, i, j + 1); b = face_node(n, f, i + 1, j + 1); c = face_node(n, f, i + 1, j);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 icosa_cells_kernel(int k, int64_t t_begin, int64_t t_end, int32_t *__restrict__ cells)
 {
-    const int64_t n = k, nn = n * n;
+    const int64_t n = k;
     for (int64_t t = t_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < t_end;
          t += (int64_t)gridDim.x * blockDim.x) {
-        int f = (int)(t / nn);
-        int64_t l = t % nn;
-        // triangles before row i: 2*n*i - i*i ; row i = largest with that <= l
-        int64_t i = (int64_t)((double)n - sqrt((double)(nn - l)));
-        if (i < 0) i = 0;
-        if (i > n - 1) i = n - 1;
-        while (i > 0 && 2 * n * i - i * i > l) --i;
-        while (i < n - 1 && 2 * n * (i + 1) - (i + 1) * (i + 1) <= l) ++i;
-        int64_t r = l - (2 * n * i - i * i);
         int32_t a, b, c;
-        if (r < n - i) {                 // up: (i,j) (i,j+1) (i+1,j)
-            int64_t j = r;
-            a = face_node(n, f, i, j); b = face_node(n, f, i, j + 1); c = face_node(n, f, i + 1, j);
-        } else {                         // down: (i,j+1) (i+1,j+1) (i+1,j)
-            int64_t j = r - (n - i);
-            a = face_node(n, f, i, j + 1); b = face_node(n, f, i + 1, j + 1); c = face_node(n, f, i + 1, j);
-        }
+        icosa_cell(n, t, a, b, c);
         int64_t o = 3 * (t - t_begin);
         cells[o] = a; cells[o + 1] = b; cells[o + 2] = c;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour rows of a vertex RANGE of the closed-form icosphere, without the cell array and without
+// any O(V) table: what build_adjacency + sort_adjacency (util.py:591-662) produce for rows
+// [v_begin, v_end), from a scan of the closed-form triangle generator (SURVEY 8e "each GPU builds
+// rows for its owned vertices ... analytic from layout").
+//   pass 1: one thread per triangle of the WHOLE mesh (no memory traffic: the triangle is computed,
+//           not read); a corner inside the range claims a slot of its vertex and stores the key
+//           (triangle index << 32 | next vertex) -- the slot an entry lands in after sorting the keys
+//           is the rank of its triangle among the triangles round the vertex, i.e. the reference's
+//           append order;
+//   pass 2: one thread per vertex of the range sorts its <= 6 keys, recomputes each incident
+//           triangle to learn the vertex BEFORE it as well, and walks the ring (util.py:623-662)
+//           on those (next, previous) pairs: two ring vertices are adjacent exactly when they are
+//           consecutive round the vertex (every 3-cycle of this mesh is a face), so `next_vert`'s
+//           membership test `i in adj[nv]` is answered by the incident triangles alone.
+// Workspace: int32 count[n] + uint64 keys[n][6] = 52 B per vertex of the RANGE.
+static inline int64_t rows_keys_offset(int64_t n) { return ((n + 1) * 4 + 15) / 16 * 16; }
+
+NXB_API int64_t nxb_mesh_icosa_adj_rows_workspace(int64_t n_rows)
+{
+    return rows_keys_offset(n_rows) + n_rows * 6 * 8;
+}
+
+__global__ void __launch_bounds__(256)
+icosa_rows_collect_kernel(int k, int64_t t_begin, int64_t t_end, int64_t v_begin, int64_t v_end,
+                          int32_t *__restrict__ count, int32_t *__restrict__ overflow, unsigned long long *__restrict__ keys)
+{
+    const int64_t n = k;
+    for (int64_t t = t_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < t_end;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int32_t v[3];
+        icosa_cell(n, t, v[0], v[1], v[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t me = v[c];
+            if (me < v_begin || me >= v_end) continue;
+            const int slot = atomicAdd(count + (me - v_begin), 1);
+            if (slot >= 6) { atomicOr(overflow, 1); continue; }
+            keys[(me - v_begin) * 6 + slot] = ((unsigned long long)t << 32) | (uint32_t)v[(c + 1) % 3];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+icosa_rows_finish_kernel(int k, int64_t v_begin, int64_t v_end, const int32_t *__restrict__ count,
+                         const unsigned long long *__restrict__ keys, int32_t *__restrict__ adj_sorted,
+                         int32_t *__restrict__ adj_unsorted)
+{
+    const int64_t nk = k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v_end - v_begin; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t idx = v_begin + i;
+        int cnt = count[i];
+        if (cnt > 6) cnt = 6;
+        unsigned long long kk[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) kk[q] = q < cnt ? keys[i * 6 + q] : ~0ull;
+#define CX(a, b) { unsigned long long lo = kk[a] < kk[b] ? kk[a] : kk[b], hi = kk[a] < kk[b] ? kk[b] : kk[a]; kk[a] = lo; kk[b] = hi; }
+        CX(0, 5) CX(1, 3) CX(2, 4)
+        CX(1, 2) CX(3, 4)
+        CX(0, 3) CX(2, 5)
+        CX(0, 1) CX(2, 3) CX(4, 5)
+        CX(1, 2) CX(3, 4)
+#undef CX
+        int32_t nx[6], pr[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            nx[q] = -1; pr[q] = -2;
+            if (q < cnt) {
+                nx[q] = (int32_t)(uint32_t)kk[q];
+                int32_t a, b, c;
+                icosa_cell(nk, (int64_t)(kk[q] >> 32), a, b, c);
+                pr[q] = (a == (int32_t)idx) ? c : ((b == (int32_t)idx) ? a : b);     // the corner before idx in (a, b, c)
+            }
+        }
+        if (adj_unsorted) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) adj_unsorted[i * 6 + q] = nx[q];
+        }
+        // ring walk, util.py:638-662 (vertices 0..11 have valence 5)
+        const int n = idx < 12 ? 5 : 6;
+        int32_t ring[6] = {-1, -1, -1, -1, -1, -1};
+        int32_t pv = (int32_t)idx, nv = nx[0];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            if (s < n - 1) {
+                ring[s] = nv;
+                // the two ring neighbours of nv round idx: the vertex before idx in the triangle whose
+                // `next` is nv, and the `next` of the triangle whose `previous` is nv
+                int32_t ra = -3, rb = -3;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    if (nx[q] == nv && nx[q] >= 0) ra = pr[q];
+                    if (pr[q] == nv) rb = nx[q];
+                }
+                // next_vert: first entry of the UNSORTED row that is adjacent to nv and is not pv
+                int32_t found = -1;
+#pragma unroll
+                for (int q = 5; q >= 0; --q) {
+                    const int32_t cand = nx[q];
+                    if (cand >= 0 && (cand == ra || cand == rb) && cand != pv) found = cand;
+                }
+                nv = found;
+                pv = ring[s];
+            }
+        }
+        if (n == 5) ring[4] = nv; else ring[5] = nv;
+        int2 *o = reinterpret_cast<int2 *>(adj_sorted + i * 6);
+        o[0] = make_int2(ring[0], ring[1]);
+        o[1] = make_int2(ring[2], ring[3]);
+        o[2] = make_int2(ring[4], ring[5]);
+    }
+}
+
+NXB_API int nxb_mesh_icosa_adj_rows(int k, int64_t v_begin, int64_t v_end, int32_t *adj_sorted, int32_t *adj_unsorted,
+                                    void *workspace, void *stream)
+{
+    NXB_ARG(k >= 1 && k <= 14000);
+    const int64_t V = 10 * (int64_t)k * k + 2, T = 20 * (int64_t)k * k;
+    NXB_ARG(0 <= v_begin && v_begin <= v_end && v_end <= V);
+    const int64_t n = v_end - v_begin;
+    if (n == 0) return NXB_OK;
+    NXB_ARG(adj_sorted && workspace && (((uintptr_t)adj_sorted) & 7) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *count = (int32_t *)workspace;
+    int32_t *overflow = count + n;
+    unsigned long long *keys = (unsigned long long *)((char *)workspace + rows_keys_offset(n));
+    NXB_CUDA(cudaMemsetAsync(workspace, 0, (size_t)rows_keys_offset(n), st));
+    // triangles that can touch the range: a range of face interiors only is touched by its own faces'
+    // triangles; the skeleton (corners, edges: ids below 12 + 30 (k-1)) is touched by every face
+    const int64_t skel = 12 + 30 * ((int64_t)k - 1), per_face = ((int64_t)k - 1) * ((int64_t)k - 2) / 2, nn = (int64_t)k * k;
+    int64_t t_begin = 0, t_end = T;
+    if (v_begin >= skel && per_face > 0) {
+        t_begin = (v_begin - skel) / per_face * nn;
+        t_end = ((v_end - 1 - skel) / per_face + 1) * nn;
+    }
+    icosa_rows_collect_kernel<<<nxb_grid_resident(icosa_rows_collect_kernel, 256, 0, (t_end - t_begin + 255) / 256), 256, 0, st>>>(
+        k, t_begin, t_end, v_begin, v_end, count, overflow, keys);
+    NXB_LAUNCH_CHECK();
+    icosa_rows_finish_kernel<<<nxb_grid_resident(icosa_rows_finish_kernel, 256, 0, (n + 255) / 256), 256, 0, st>>>(
+        k, v_begin, v_end, count, keys, adj_sorted, adj_unsorted);
+    NXB_LAUNCH_CHECK();
+    int32_t flag = 0;
+    NXB_CUDA(cudaMemcpyAsync(&flag, overflow, sizeof flag, cudaMemcpyDeviceToHost, st));
+    NXB_CUDA(cudaStreamSynchronize(st));
+    if (flag) { nxb_set_error("nxb_mesh_icosa_adj_rows: a vertex has more than 6 outgoing edges"); return NXB_ERR_OVERFLOW; }
+    return NXB_OK;
 }
 
 NXB_API int nxb_mesh_icosa_points(int k, int64_t v_begin, int64_t v_end, nxb_float4 *xyz_f32, double *xyz_f64, void *stream)

@@ -171,16 +171,21 @@ fbm_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ xyz, in
 }
 
 // ---- branch-free 3-D fBm (nxb_noise3_fast.cuh): one 1024-thread CTA per SM, 128.6 KB of
-// conflict-free tables in shared memory, persistent grid-stride over the vertices.
+// conflict-free tables in shared memory, persistent grid-stride over the vertices.  Positions are
+// float64 (the reference's `verts`, terrain.py:17) or float4 promoted to float64; the per-octave
+// lattice coordinate, the cell and the candidate selection are float64 (exactly the reference's
+// decisions), the contributions FP32.
 struct FbmFastParams {
-    float freq[NXB_MAX_OCT];
+    double nr[NXB_MAX_OCT];     // n_freq / world_radius (terrain.py:43), applied to scale * position
     float amp[NXB_MAX_OCT];     // 0.5 * amplitude / 103   (noise3d = v / 103, terrain.py:28)
+    double scale;               // nixis.py:249 `points *= world_radius` for positions stored on the unit sphere
     float base;                 // sum of 0.5 * amplitude
     int n_oct;
 };
 
+template <bool POS64>
 __global__ void __launch_bounds__(1024, 1)
-fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ xyz, int64_t n,
+fbm3_fast_kernel(const NxbTables *__restrict__ tab, const void *__restrict__ pos, int64_t n,
                  const __grid_constant__ FbmFastParams prm, const float *__restrict__ init,
                  float *__restrict__ out, float *__restrict__ minmax)
 {
@@ -200,12 +205,19 @@ fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ x
         const int64_t vv = base + (threadIdx.x & 31u);
         const bool live = vv < n;
         const int64_t v = live ? vv : n - 1;
-        const float4 p = __ldg(xyz + v);
+        double px, py, pz;
+        if (POS64) {
+            const double *p = static_cast<const double *>(pos) + 3 * v;
+            px = __dmul_rn(__ldg(p), prm.scale); py = __dmul_rn(__ldg(p + 1), prm.scale); pz = __dmul_rn(__ldg(p + 2), prm.scale);
+        } else {
+            const float4 p = __ldg(static_cast<const float4 *>(pos) + v);
+            px = __dmul_rn((double)p.x, prm.scale); py = __dmul_rn((double)p.y, prm.scale); pz = __dmul_rn((double)p.z, prm.scale);
+        }
         float acc = init ? init[v] : 0.0f;
 #pragma unroll 1
         for (int o = 0; o < prm.n_oct; ++o) {
-            const float f = prm.freq[o];
-            acc = fmaf(nxf_noise3_x103(p.x * f, p.y * f, p.z * f, nxf_sm, lane4), prm.amp[o], acc);
+            const double f = prm.nr[o];                 // terrain.py:17 `verts * n_roughness`
+            acc = fmaf(nxf_noise3_x103_d(__dmul_rn(px, f), __dmul_rn(py, f), __dmul_rn(pz, f), nxf_sm, lane4), prm.amp[o], acc);
         }
         acc += prm.base;
         if (live) out[v] = acc;
@@ -217,35 +229,65 @@ fbm3_fast_kernel(const NxbTables *__restrict__ tab, const float4 *__restrict__ x
 
 static bool g_fbm_fast_attr[64] = {false};
 
-static int fbm3_fast_launch(void *tables, const nxb_float4 *xyz_unit, int64_t n, int cnt,
-                            const double *freq_host, const double *amp_host,
+// nr_host[o]: n_freq_o / world_radius; amp_host[o]: octave amplitude in output units (n_strength * radius)
+static int fbm3_fast_launch(void *tables, const void *pos, bool pos64, double scale, int64_t n, int cnt,
+                            const double *nr_host, const double *amp_host,
                             const float *init, float *out, float *minmax, cudaStream_t st)
 {
     FbmFastParams prm;
     memset(&prm, 0, sizeof prm);
     double base = 0.0;
     for (int o = 0; o < cnt; ++o) {
-        prm.freq[o] = (float)freq_host[o];
+        prm.nr[o] = nr_host[o];
         prm.amp[o] = (float)(0.5 * amp_host[o] / 103.0);
         base += 0.5 * amp_host[o];
     }
     prm.base = (float)base;
+    prm.scale = scale;
     prm.n_oct = cnt;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !g_fbm_fast_attr[dev]) {
-        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NXF_SMEM_BYTES + 32768)));
+        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NXF_SMEM_BYTES + 32768)));
+        NXB_CUDA(cudaFuncSetAttribute(fbm3_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NXF_SMEM_BYTES + 32768)));
         g_fbm_fast_attr[dev] = true;
     }
-    int grid = nxb_grid_resident(fbm3_fast_kernel, 1024, NXF_SMEM_BYTES + 32768, (n + 1023) / 1024);
-    fbm3_fast_kernel<<<grid, 1024, NXF_SMEM_BYTES + 32768, st>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, init, out, minmax);
+    if (pos64) {
+        int grid = nxb_grid_resident(fbm3_fast_kernel<true>, 1024, NXF_SMEM_BYTES + 32768, (n + 1023) / 1024);
+        fbm3_fast_kernel<true><<<grid, 1024, NXF_SMEM_BYTES + 32768, st>>>((const NxbTables *)tables, pos, n, prm, init, out, minmax);
+    } else {
+        int grid = nxb_grid_resident(fbm3_fast_kernel<false>, 1024, NXF_SMEM_BYTES + 32768, (n + 1023) / 1024);
+        fbm3_fast_kernel<false><<<grid, 1024, NXF_SMEM_BYTES + 32768, st>>>((const NxbTables *)tables, pos, n, prm, init, out, minmax);
+    }
     NXB_LAUNCH_CHECK();
     return NXB_OK;
 }
 
-static int fbm_launch(int dim, void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
-                      const double *freq_host, const double *amp_host, const double *w_host,
-                      const float *init, float *out, float *minmax, void *stream)
+// 3-D fBm in chunks of NXB_MAX_OCT octaves accumulated through `out`
+static int fbm3_run(void *tables, const void *pos, bool pos64, double scale, int64_t n, int n_oct,
+                    const double *nr_host, const double *amp_host, const float *init, float *out, float *minmax, void *stream)
+{
+    NXB_ARG(tables && n >= 0 && n_oct >= 0);
+    if (n == 0) return NXB_OK;
+    NXB_ARG(pos && out && (n_oct == 0 || (nr_host && amp_host)));
+    const float *cur_init = init;
+    int done = 0;
+    do {
+        const int cnt = n_oct - done < NXB_MAX_OCT ? n_oct - done : NXB_MAX_OCT;
+        for (int o = 0; o < cnt; ++o)
+            NXB_ARG(fabs(nr_host[done + o] * scale) * 1.75 < NXF_MAX_COORD);        // unit-sphere positions assumed
+        float *mm = (done + cnt >= n_oct) ? minmax : nullptr;
+        int rc = fbm3_fast_launch(tables, pos, pos64, scale, n, cnt, nr_host + done, amp_host + done, cur_init, out, mm, (cudaStream_t)stream);
+        if (rc) return rc;
+        done += cnt;
+        cur_init = out;
+    } while (done < n_oct);
+    return NXB_OK;
+}
+
+static int fbm4_launch(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
+                       const double *freq_host, const double *amp_host, const double *w_host,
+                       const float *init, float *out, float *minmax, void *stream)
 {
     NXB_ARG(tables && n >= 0 && n_oct >= 0);
     if (n == 0) return NXB_OK;
@@ -263,23 +305,8 @@ static int fbm_launch(int dim, void *tables, const nxb_float4 *xyz_unit, int64_t
         }
         prm.n_oct = cnt;
         float *mm = (done + cnt >= n_oct) ? minmax : nullptr;
-        // the branch-free kernel floors with the magic-number trick: lattice coordinates must stay
-        // below 2^21 (unit-sphere positions: |x| + |stretch| <= 1.75 * freq)
-        double fmax = 0.0;
-        for (int o = 0; o < cnt; ++o) fmax = fabs(freq_host[done + o]) > fmax ? fabs(freq_host[done + o]) : fmax;
-        if (dim == 3 && cnt > 0 && fmax * 1.75 < (double)NXF_MAX_COORD && !getenv("NXB_FBM_V1")) {
-            int rc = fbm3_fast_launch(tables, xyz_unit, n, cnt, freq_host + done, amp_host + done, cur_init, out, mm, (cudaStream_t)stream);
-            if (rc) return rc;
-            done += cnt;
-            cur_init = out;
-            continue;
-        }
-        int grid = dim == 3 ? nxb_grid_resident(fbm_kernel<3>, 256, 0, (n + 255) / 256)
-                            : nxb_grid_resident(fbm_kernel<4>, 256, 0, (n + 255) / 256);
-        if (dim == 3)
-            fbm_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, cur_init, out, mm);
-        else
-            fbm_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, cur_init, out, mm);
+        int grid = nxb_grid_resident(fbm_kernel<4>, 256, 0, (n + 255) / 256);
+        fbm_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const NxbTables *)tables, (const float4 *)xyz_unit, n, prm, cur_init, out, mm);
         NXB_LAUNCH_CHECK();
         done += cnt;
         cur_init = out;
@@ -291,7 +318,14 @@ NXB_API int nxb_fbm3_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, in
                          const double *freq_host, const double *amp_host,
                          const float *init, float *out, float *minmax, void *stream)
 {
-    return fbm_launch(3, tables, xyz_unit, n, n_oct, freq_host, amp_host, nullptr, init, out, minmax, stream);
+    return fbm3_run(tables, xyz_unit, false, 1.0, n, n_oct, freq_host, amp_host, init, out, minmax, stream);
+}
+
+NXB_API int nxb_fbm3_pos64_f32(void *tables, const double *verts, double scale, int64_t n, int n_oct,
+                               const double *nr_host, const double *amp_host,
+                               const float *init, float *out, float *minmax, void *stream)
+{
+    return fbm3_run(tables, verts, true, scale, n, n_oct, nr_host, amp_host, init, out, minmax, stream);
 }
 
 NXB_API int nxb_fbm4_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, int n_oct,
@@ -303,5 +337,5 @@ NXB_API int nxb_fbm4_f32(void *tables, const nxb_float4 *xyz_unit, int64_t n, in
     nxb_set_error("noise4 not built");
     return NXB_ERR_UNSUPPORTED;
 #endif
-    return fbm_launch(4, tables, xyz_unit, n, n_oct, freq_host, amp_host, w_host, init, out, minmax, stream);
+    return fbm4_launch(tables, xyz_unit, n, n_oct, freq_host, amp_host, w_host, init, out, minmax, stream);
 }

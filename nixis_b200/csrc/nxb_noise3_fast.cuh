@@ -20,7 +20,10 @@
 //     Values of the permutation table are stored pre-multiplied by the row pitch (128 B), the
 //     last hash level indexes three float tables holding the gradient components directly
 //     (GRADIENTS_3D[perm_grad_index_3D[h]], opensimplex.py:123-130): no decode arithmetic.
-//   * floor() uses the 1.5*2^23 magic-number trick (exact for |x| < 2^22), no F2I/I2F.
+//   * round 2: lattice cell, in-cell coordinates and the whole candidate selection are float64
+//     (nxf_noise3_x103_d): same comparisons on the reference's own quantities, so the candidate
+//     set is the reference's bit for bit; they issue on the otherwise idle FP64 pipe.  floor()
+//     uses the 1.5*2^52 magic-number trick (exact for |x| < 2^51), no F2I/I2F.
 //
 // This header is plain C++ apart from a few intrinsics so that tools/host_noise_check.cpp can
 // compile it with g++ and compare against the float64 oracle without a GPU.
@@ -50,7 +53,7 @@ static inline uint32_t nxf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); ret
 #define NXF_OFF_GZ (3u * NXF_TAB_BYTES)
 #define NXF_OFF_EXT (4u * NXF_TAB_BYTES)        // 19 extra records x 32 B (not replicated)
 #define NXF_SMEM_BYTES (NXF_OFF_EXT + 32u * 20u)
-#define NXF_MAX_COORD 2000000.0f        // |lattice coordinate| bound for the magic-number floor
+#define NXF_MAX_COORD 1.0e9              // |lattice coordinate| bound (the hash keeps the low 32 bits of the integer part)
 
 // record of one non-cube extra lattice point: displacement constants (offset + m/3), the live
 // constant T (2, or -16 for "no extra"), hash offsets pre-multiplied by the row pitch
@@ -220,6 +223,9 @@ NXF_DEV void nxf_select_branchy(float fx, float fy, float fz, float fsum,
     }
 }
 
+NXF_DEV float nxf_abs(float v) { return fabsf(v); }
+NXF_DEV double nxf_abs(double v) { return fabs(v); }
+
 #ifdef __CUDACC__
 #define NXF_ANY(p) __any_sync(0xffffffffu, (p))
 #else
@@ -234,24 +240,32 @@ NXF_DEV void nxf_select_branchy(float fx, float fy, float fz, float fsum,
 //     extra codes / live corners are computed arithmetically from them;
 //   * the two blocks are skipped with a warp vote when no lane of the warp needs them, so a
 //     coherent warp pays for one block, a mixed warp for both, and no lane ever idles.
-NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
-                        float &T000, float &T100, float &T010, float &T001,
-                        float &T110, float &T101, float &T011, float &T111, int &e0, int &e1)
+//
+// R = float: the FP32 selection of round 1.  R = double: the SAME comparisons on the reference's
+// own float64 quantities -- the candidate set is then the reference's, bit for bit, ties included;
+// only predicates leave this routine, so no 64-bit value is ever selected or stored.
+template <typename R>
+NXF_DEV void nxf_select_r(R fx, R fy, R fz, R fsum,
+                          float &T000, float &T100, float &T010, float &T001,
+                          float &T110, float &T101, float &T011, float &T111, int &e0, int &e1)
 {
     const float LIVE = 2.0f, DEAD = -16.0f;
-    const bool r0 = fsum <= 1.0f, r1 = fsum >= 2.0f, tet = r0 || r1;
+    const bool r0 = fsum <= (R)1, r1 = fsum >= (R)2, tet = r0 || r1;
     // outputs of the tetrahedron block
     int te0 = 18, te1 = 18; bool opt0 = false, opt1 = false, opt2 = false;
     if (NXF_ANY(tet)) {
-        const float s0 = r1 ? -fx : fx, s1 = r1 ? -fy : fy, s2 = r1 ? -fz : fz;
-        const float w = r1 ? fsum - 3.0f : 1.0f - fsum;
-        const bool ge = s0 >= s1;
-        const bool c1 = ge && s2 > s1;                  // newcomer replaces b
-        const bool c2 = !ge && s2 > s0;                 // newcomer replaces a
-        const float as = c2 ? s2 : s0, bs = c1 ? s2 : s1;
-        const int ia = c2 ? 2 : 0, ib = c1 ? 2 : 1;
-        const bool caseA = (w > as) || (w > bs);
-        const int cs = (bs > as) ? ib : ia;             // the single closest candidate (case A)
+        // tet1 = tet0 with negated scores (exact); 1 - fsum == -(fsum - 1) and 3 - fsum == -(fsum - 3) exactly
+        const R s0 = r1 ? -fx : fx, s1 = r1 ? -fy : fy, s2 = r1 ? -fz : fz;
+        const R wm = fsum - (r1 ? (R)3 : (R)1);
+        const R w = r1 ? wm : -wm;
+        const bool ge = s0 >= s1, g21 = s2 > s1, g20 = s2 > s0, g12 = s1 > s2;
+        const bool w0 = w > s0, w1 = w > s1, w2 = w > s2;
+        const bool c1 = ge && g21;                      // newcomer replaces b
+        const bool c2 = !ge && g20;                     // newcomer replaces a
+        const int ia = c2 ? 2 : 0, ib = c1 ? 2 : 1;     // as = s[ia], bs = s[ib]
+        const bool caseA = (c2 ? w2 : w0) || (c1 ? w2 : w1);
+        const bool bgta = c1 ? g20 : (c2 ? g12 : !ge);  // bs > as
+        const int cs = bgta ? ib : ia;                  // the single closest candidate (case A)
         const int io = 3 - ia - ib;                     // the axis not among the two closest (case B)
         // tet0: A -> extras 2cs, 2cs+1;            B -> cube corner omitting io + (1,1,1)-2e_io (12+io)
         // tet1: A -> extras 10-2cs, 11-2cs;        B -> cube corner e_io         + 2e_io       (15+io)
@@ -264,9 +278,11 @@ NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
     // outputs of the octahedron block
     int oe0 = 18, oe1 = 18; bool near2 = false, far2 = false;
     if (NXF_ANY(!tet)) {
-        const float p1 = fx + fy, p2 = fx + fz, p3 = fy + fz;
-        const bool f1 = p1 > 1.0f, f2 = p2 > 1.0f, f3 = p3 > 1.0f;
-        const float q1 = fabsf(p1 - 1.0f), q2 = fabsf(p2 - 1.0f), q3 = fabsf(p3 - 1.0f);
+        const R p1 = fx + fy, p2 = fx + fz, p3 = fy + fz;
+        const bool f1 = p1 > (R)1, f2 = p2 > (R)1, f3 = p3 > (R)1;
+        // |p - 1| is the reference's `p - 1` (p > 1) or `1 - p` (else): the same rounded value
+        const R d1 = p1 - (R)1, d2 = p2 - (R)1, d3 = p3 - (R)1;
+        const R q1 = nxf_abs(d1), q2 = nxf_abs(d2), q3 = nxf_abs(d3);
         // reference: a <- p1, b <- p2; p3 replaces a if (as <= bs && as < sc), else b if (as > bs && bs < sc)
         const bool le = q1 <= q2;
         const bool ra = le && q1 < q3;
@@ -294,42 +310,17 @@ NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
     T110 = (!r0 || opt2) ? LIVE : DEAD;
 }
 
-// x,y,z: lattice-space coordinates (vertex * octave frequency).  Returns noise3d * 103.
-NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_t lane4)
+NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
+                        float &T000, float &T100, float &T010, float &T001,
+                        float &T110, float &T101, float &T011, float &T111, int &e0, int &e1)
 {
-    const float MAGIC = 12582912.0f;   // 1.5 * 2^23: (x + MAGIC) - MAGIC rounds to nearest integer
-    const float so = (x + y + z) * (-1.0f / 6.0f);
-    const float xs = x + so, ys = y + so, zs = z + so;
-    const float tx = xs + MAGIC, ty = ys + MAGIC, tz = zs + MAGIC;
-    float bx = tx - MAGIC, by = ty - MAGIC, bz = tz - MAGIC;
-    // floor = round-to-nearest, minus 1 where that rounded up (opensimplex.py:18-21)
-    const bool ux = bx > xs, uy = by > ys, uz = bz > zs;
-    bx = ux ? bx - 1.0f : bx; by = uy ? by - 1.0f : by; bz = uz ? bz - 1.0f : bz;
-    NxfCtx c;
-    c.sm = sm; c.lane4 = lane4;
-    // low mantissa bits of (x + MAGIC) are the integer; only bits 0..7 survive the masks
-    c.xb7 = (nxf_as_uint(tx) - (ux ? 1u : 0u)) << 7;
-    c.yb7 = (nxf_as_uint(ty) - (uy ? 1u : 0u)) << 7;
-    c.zb7 = (nxf_as_uint(tz) - (uz ? 1u : 0u)) << 7;
-    const float fx = xs - bx, fy = ys - by, fz = zs - bz;
-    const float fsum = fx + fy + fz;
-    // position relative to the cell origin: f + fsum/3 (the un-skew of the in-cell coordinates;
-    // the reference's x - xb, opensimplex.py:283-297, is the same quantity)
-    c.dx0 = nxf_fma(fsum, 1.0f / 3.0f, fx);
-    c.dy0 = nxf_fma(fsum, 1.0f / 3.0f, fy);
-    c.dz0 = nxf_fma(fsum, 1.0f / 3.0f, fz);
-    c.v = 0.0f;
+    nxf_select_r<float>(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
+}
 
-    // ---- selection: live constants of the 8 cube corners + two extra codes ------------------
-    float T000, T100, T010, T001, T110, T101, T011, T111;
-    int e0, e1;
-#ifdef NXF_SELECT_BRANCHY
-    nxf_select_branchy(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
-#else
-    nxf_select(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
-#endif
-
-    // ---- the 8 cube corners: shared hash tree (2 + 4 lookups), then one leaf each -----------
+// the 8 cube corners: shared hash tree (2 + 4 lookups), one leaf each; then the two non-cube extras
+NXF_DEV float nxf_contributions(NxfCtx &c, float T000, float T100, float T010, float T001,
+                                float T110, float T101, float T011, float T111, int e0, int e1)
+{
     const uint32_t hx0 = nxf_hash(c, c.xb7), hx1 = nxf_hash(c, c.xb7 + NXF_ROW);
     const uint32_t h00 = nxf_hash(c, hx0 + c.yb7), h01 = nxf_hash(c, hx0 + c.yb7 + NXF_ROW);
     const uint32_t h10 = nxf_hash(c, hx1 + c.yb7), h11 = nxf_hash(c, hx1 + c.yb7 + NXF_ROW);
@@ -344,6 +335,56 @@ NXF_DEV float nxf_noise3_x103(float x, float y, float z, const char *sm, uint32_
     nxf_extra(c, e0);
     nxf_extra(c, e1);
     return c.v;
+}
+
+// ---- float64 prologue + selection (device: __dadd_rn / __dmul_rn are never contracted into FMAs;
+// host build of this header: plain double arithmetic, compile with -ffp-contract=off) -----------
+#ifdef __CUDACC__
+#define nxf_dadd(a, b) __dadd_rn(a, b)
+#define nxf_dmul(a, b) __dmul_rn(a, b)
+#define nxf_dlo(d) ((uint32_t)__double2loint(d))
+#else
+#define nxf_dadd(a, b) ((a) + (b))
+#define nxf_dmul(a, b) ((a) * (b))
+static inline uint32_t nxf_dlo(double d) { uint64_t u; memcpy(&u, &d, 8); return (uint32_t)u; }
+#endif
+
+// x,y,z: the reference's float64 noise3d arguments (opensimplex.py:266).  Lattice cell, in-cell
+// coordinates and every comparison of the candidate selection are evaluated in float64, operation
+// for operation as the reference does (opensimplex.py:270-300 and the region tests) -- they run on
+// the FP64 pipe, which this kernel leaves idle otherwise -- so the candidate set is the reference's
+// own, exact ties included.  The contributions (displacements, attn^4 * gradient dot) are FP32.
+// Returns noise3d * 103.
+NXF_DEV float nxf_noise3_x103_d(double x, double y, double z, const char *sm, uint32_t lane4)
+{
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: (x + MAGIC) - MAGIC rounds to nearest integer
+    const double so = nxf_dmul(nxf_dadd(nxf_dadd(x, y), z), -1.0 / 6);          // opensimplex.py:270 stretch_offset
+    const double xs = nxf_dadd(x, so), ys = nxf_dadd(y, so), zs = nxf_dadd(z, so);
+    const double tx = nxf_dadd(xs, MAGIC), ty = nxf_dadd(ys, MAGIC), tz = nxf_dadd(zs, MAGIC);
+    double bx = nxf_dadd(tx, -MAGIC), by = nxf_dadd(ty, -MAGIC), bz = nxf_dadd(tz, -MAGIC);
+    // floor = round-to-nearest, minus 1 where that rounded up (fastfloor, opensimplex.py:18-21; exact for |x| < 2^51)
+    const bool ux = bx > xs, uy = by > ys, uz = bz > zs;
+    bx = nxf_dadd(bx, ux ? -1.0 : 0.0); by = nxf_dadd(by, uy ? -1.0 : 0.0); bz = nxf_dadd(bz, uz ? -1.0 : 0.0);
+    NxfCtx c;
+    c.sm = sm; c.lane4 = lane4;
+    // low mantissa bits of (xs + MAGIC) are the integer; only bits 0..7 survive the masks
+    c.xb7 = (nxf_dlo(tx) - (ux ? 1u : 0u)) << 7;
+    c.yb7 = (nxf_dlo(ty) - (uy ? 1u : 0u)) << 7;
+    c.zb7 = (nxf_dlo(tz) - (uz ? 1u : 0u)) << 7;
+    const double fx = nxf_dadd(xs, -bx), fy = nxf_dadd(ys, -by), fz = nxf_dadd(zs, -bz);   // :285-287 xins..
+    const double fsum = nxf_dadd(nxf_dadd(fx, fy), fz);                           // :290 in_sum
+    // position relative to the cell origin, dx0 = x - xb (opensimplex.py:279-295): in exact arithmetic
+    // x - (xsb + (xsb+ysb+zsb)/3) = xins + in_sum/3 (the un-skew of the in-cell coordinates), which
+    // needs no large-number cancellation and is taken in FP32 -- it only feeds the FP32 contributions
+    const float fsum_f = (float)fsum;
+    c.dx0 = nxf_fma(fsum_f, 1.0f / 3.0f, (float)fx);
+    c.dy0 = nxf_fma(fsum_f, 1.0f / 3.0f, (float)fy);
+    c.dz0 = nxf_fma(fsum_f, 1.0f / 3.0f, (float)fz);
+    c.v = 0.0f;
+    float T000, T100, T010, T001, T110, T101, T011, T111;
+    int e0, e1;
+    nxf_select_r<double>(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
+    return nxf_contributions(c, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
 }
 
 // Fill the replicated tables.  perm8 / grad8 as in NxbTables (nxb_noise.cuh).  Called by every

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import runtime as rt
+from . import shard
 from .util import DeviceMesh
 
 RAIN_AMOUNT = 0.3 / 320         # erosion.py:182
@@ -64,8 +65,13 @@ class Erosion3State:
         self.iterations += 1
 
     def run(self, num_iter, rain=RAIN_AMOUNT):
-        for _ in range(num_iter):
-            self.step(rain)
+        """num_iter sweeps issued by the C-side loop (nxb_erode3_run_f32)."""
+        if num_iter <= 0:
+            return
+        res = rt.erode3_run(self.plan, self.dist, self.cur, self.nxt, rain, num_iter)
+        if res is self.nxt:
+            self.cur, self.nxt = self.nxt, self.cur
+        self.iterations += num_iter
 
     @property
     def heights(self):
@@ -109,28 +115,94 @@ def _erode_terrain3_exact(nodes, neighbors, heights, num_iter, return_state):
     return None
 
 
+def _snapshot(st, i):
+    """erosion.py:186-192: a grayscale map of the heights after sweep i (rescale(heights, 0, 255) blended
+    through the nearest-vertex query of the export path, nixis.py:270-283) saved as
+    `erosion_snapshot_<iii>` in cfg.SNAP_DIR.  The heights stay on the device: one fused map kernel
+    (rescale + 3-vertex blend) per snapshot."""
+    import os
+    from . import util
+    cfg = util.cfg
+    if cfg.IMG_QUERY_DATA is None:
+        raise ValueError("erode_terrain3(snapshot=True) needs cfg.IMG_QUERY_DATA (nixis.py:283: the nearest-vertex "
+                         "query of every pixel); run util.build_KDTree / KDT.query first")
+    dists, ids = cfg.IMG_QUERY_DATA[0], cfg.IMG_QUERY_DATA[1]
+    d = dists if isinstance(dists, torch.Tensor) else rt.upload(np.ascontiguousarray(dists, dtype=np.float64))
+    n = ids if isinstance(ids, torch.Tensor) else rt.upload(np.ascontiguousarray(ids, dtype=np.int64))
+    h = st.heights.contiguous()
+    lo, hi = (float(v) for v in rt.minmax(h).tolist())
+    img = rt.idw_map(d, n, h, lo, hi, 0.0, 255.0, out_bits=8)
+    snap_dir = cfg.SNAP_DIR or os.getcwd()
+    util.save_image({f"{i + 1:03d}": img}, snap_dir, "erosion_snapshot")
+
+
+def _erode_terrain3_sharded(ctx, nodes, neighbors, heights, num_iter, return_state):
+    """One rank's slice under a shard context (shard.py): halo plan from the rows given, halo positions
+    fetched once for the edge lengths, then the sharded sweep loop with the fused exchange."""
+    from .multigpu import ShardedErosion
+    from .partition import build_rank_plan_local, exchange_halo_torch
+    rows = _neighbors(neighbors)
+    plan = build_rank_plan_local(rows, ctx.rank, ctx.world, ctx.ranges, group=ctx.group)
+    own64 = nodes if isinstance(nodes, torch.Tensor) else rt.upload(np.ascontiguousarray(nodes, dtype=np.float64))
+    assert own64.dtype == torch.float64 and own64.shape == (plan.n_own, 3), "nodes must be this rank's float64 [n_own,3] slice"
+    comps = []
+    for a in range(3):                  # positions of the halo vertices come from their owners, once
+        c = torch.zeros(plan.capacity, dtype=torch.float64, device=own64.device)
+        c[: plan.n_own] = own64[:, a]
+        comps.append(c)
+    exchange_halo_torch(plan, comps, group=ctx.group)
+    dist_f32 = rt.edge_lengths(torch.stack(comps, dim=1).contiguous(), plan.local_adj)
+    del comps
+    ero = ShardedErosion(plan, dist_f32, transport="fused", group=ctx.group)
+    dev_io = isinstance(heights, torch.Tensor)
+    ero.load(heights if dev_io else rt.upload_f32(heights))
+    ero.run(num_iter)
+    ero.finish()
+    try:
+        if dev_io:
+            return (ero.heights.clone(), ero.water.clone(), ero.sediment.clone()) if return_state else ero.heights.clone()
+        rt.download_f64(ero.heights.contiguous(), out=heights)
+        if return_state:
+            return rt.download_f64(ero.water.contiguous()), rt.download_f64(ero.sediment.contiguous())
+        return None
+    finally:
+        ero.close()
+
+
 def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbose=True, return_state=False, exact=False):
     """erosion.py:172-192.  exact=True: float64 kernel without FMA in the reference's operation order,
-    bit-identical to the reference (slower: double state, global gathers); default FP32 tile-plan kernel.  `heights` (numpy float64) is eroded IN PLACE and None is returned;
-    with CUDA tensors the new height tensor is returned.  water / sediment start at zero and are
-    discarded unless return_state=True.  `snapshot` (per-iteration PNG export) is outside the hot
-    path and not supported."""
-    if snapshot:
-        raise NotImplementedError("erosion snapshots use the image-export path, which is out of scope")
+    bit-identical to the reference (slower: double state, global gathers); default FP32 tile-plan kernel.
+    `heights` (numpy float64) is eroded IN PLACE and None is returned; with CUDA tensors the new height
+    tensor is returned.  water / sediment start at zero and are discarded unless return_state=True.
+    snapshot=True saves a grayscale map after every sweep (erosion.py:186-192; needs cfg.IMG_QUERY_DATA).
+    Under a shard context (shard.set_shard) the arguments are this rank's slices and the sweeps run
+    sharded with the NVLink halo exchange."""
     if verbose:
         print("Starting terrain erosion...")
     if num_iter <= 0:
         num_iter = 1
+    ctx = shard.current()
+    if ctx is not None and ctx.world > 1:
+        if exact or snapshot:
+            raise ValueError("exact / snapshot modes of erode_terrain3 are single-process")
+        return _erode_terrain3_sharded(ctx, nodes, neighbors, heights, num_iter, return_state)
     if exact:
         return _erode_terrain3_exact(nodes, neighbors, heights, num_iter, return_state)
     adj = _neighbors(neighbors)
     dev_io = isinstance(heights, torch.Tensor)
     h32 = heights if dev_io else rt.upload_f32(heights)
     st = Erosion3State(nodes, adj, h32)
-    for i in range(num_iter):
-        if verbose:
-            print("  Erosion pass:", i + 1, "of", num_iter)
-        st.step()
+    if snapshot:
+        for i in range(num_iter):
+            if verbose:
+                print("  Erosion pass:", i + 1, "of", num_iter)
+            st.step()
+            _snapshot(st, i)
+    else:
+        if verbose:                     # launches are asynchronous: the progress lines are all there is to see
+            for i in range(num_iter):
+                print("  Erosion pass:", i + 1, "of", num_iter)
+        st.run(num_iter)                # the whole loop in one C call
     if dev_io:
         return st if return_state else st.heights
     rt.download_f64(st.heights.contiguous(), out=heights)

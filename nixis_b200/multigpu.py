@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from . import _lib
 from . import runtime as rt
-from .partition import RankPlan, build_rank_plan, exchange_halo_torch, round_up, vertex_ranges, TILE
+from .partition import RankPlan, build_rank_plan, build_rank_plan_local, exchange_halo_torch, round_up, vertex_ranges, TILE
 from .pipeline import Collective, assemble_heights, N_INIT_ROUGH, N_INIT_STRENGTH, N_ROUGHNESS, N_PERSISTENCE
 from .util import DeviceMesh
 
@@ -36,6 +36,78 @@ def _i64_array(values):
     return (C.c_int64 * len(values))(*[int(v) for v in values])
 
 
+class _RawCuda:
+    """A cudaMalloc'ed range as a torch-importable object (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerMemory:
+    """One float32 buffer per rank that every rank of the group can store to from its kernels.
+    kind "symm": torch.distributed._symmetric_memory (plumbing); kind "ipc": cudaMalloc + CUDA IPC
+    handles exchanged through the process group (csrc/nxb_halo.cu nxb_peer_*), which also works when
+    several ranks share one device.  `ptrs[r]` is rank r's buffer as seen from this process."""
+
+    def __init__(self, n_floats, device, group, kind):
+        self.kind, self.group = kind, group
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self._opened = []
+        self._own = None
+        if kind == "symm":
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(int(n_floats), dtype=torch.float32, device=device)
+            self._hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            buf.zero_()
+            self.buf = buf
+            self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        elif kind == "ipc":
+            ptr = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            _lib.call("nxb_peer_alloc", int(n_floats) * 4, C.byref(ptr), handle)
+            self._own = ptr.value
+            self._raw = _RawCuda(ptr.value, n_floats)
+            self.buf = torch.as_tensor(self._raw, device=device)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.ptrs = []
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self._own)
+                    continue
+                p = C.c_void_p()
+                _lib.call("nxb_peer_open", (C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p))
+                self._opened.append(p.value)
+                self.ptrs.append(p.value)
+        else:
+            raise ValueError(kind)
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (ipc kind; collective: everybody calls it)."""
+        if self.kind != "ipc" or self._own is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            _lib.call("nxb_peer_close", C.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=self.group)
+        self.buf = None
+        _lib.call("nxb_peer_free", C.c_void_p(self._own))
+        self._own = None
+
+
+def _is_gloo(group):
+    try:
+        return dist.get_backend(group) == "gloo"
+    except Exception:
+        return False
+
+
+MAX_PEERS = 8       # csrc/nxb_erosion.cu ERO_MAX_PEERS, csrc/nxb_halo.cu HALO_MAX_PEERS
+MAX_FLAGS = 64      # flag slots behind the state buffers (one per source rank)
+
+
 class ShardedErosion:
     """Erosion state of one rank: padded own range + halo slots, ping-pong (h, w, s)."""
 
@@ -47,39 +119,57 @@ class ShardedErosion:
         self.dist = dist_f32
         self.tile_plan = rt.ErosionPlan(plan.local_adj, capacity=plan.capacity)
         # symmetric sizes: every rank allocates the max capacity so that offsets agree
-        cap_t = torch.tensor([plan.capacity], dtype=torch.int64, device=dev)
+        cap_t = torch.tensor([plan.capacity], dtype=torch.int64, device="cpu" if _is_gloo(group) else dev)
         if self.world > 1:
             dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
         self.cap = int(cap_t.item())
-        self.transport = transport if self.world > 1 else "none"
+        self.send_peers = sorted(plan.send_idx)
+        self.recv_peers = sorted(plan.recv_slice)
+        transport = transport if self.world > 1 else "none"
+        if transport in ("nvlink", "fused"):
+            # the kernels hold at most MAX_PEERS peer pointers and the flag array has MAX_FLAGS slots:
+            # beyond that (world > 9 can touch more than 8 peers through the mesh skeleton) use p2p
+            too_many = torch.tensor([int(len(self.send_peers) > MAX_PEERS or len(self.recv_peers) > MAX_PEERS
+                                         or self.world > MAX_FLAGS)], dtype=torch.int64, device=cap_t.device)
+            dist.all_reduce(too_many, op=dist.ReduceOp.MAX, group=group)
+            if int(too_many.item()):
+                transport = "p2p"
         self.sweeps = 0                     # total sweeps since creation (flag values)
-        self.flag_base = 0
         n_state = 4 * self.cap              # hA wA hB wB
-        if self.transport in ("nvlink", "fused"):
-            import torch.distributed._symmetric_memory as symm
-            self._symm = symm
-            try:
-                buf = symm.empty(int(n_state + 64), dtype=torch.float32, device=dev)
-            except Exception as exc:
-                raise RuntimeError(f"symmetric memory allocation failed on rank {self.rank}: n={n_state + 64} "
-                                   f"cap={self.cap} plan.capacity={plan.capacity} dev={dev}: {exc}") from exc
-            self._hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
-            buf.zero_()
-            self._buf = buf
-            self._peer_base = [int(p) for p in self._hdl.buffer_ptrs]
+        self.peer_mem = None
+        if transport in ("nvlink", "fused"):
+            kinds = [os.environ.get("NXB_PEER_MEM")] if os.environ.get("NXB_PEER_MEM") else \
+                    (["ipc"] if _is_gloo(group) else ["symm", "ipc"])
+            err = None
+            for kind in kinds:
+                try:
+                    self.peer_mem = PeerMemory(n_state + MAX_FLAGS, dev, group, kind)
+                    break
+                except Exception as exc:            # noqa: BLE001 -- fall through to the next mechanism
+                    err = exc
+            ok = torch.tensor([int(self.peer_mem is not None)], dtype=torch.int64, device=cap_t.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if not int(ok.item()):
+                if self.peer_mem is not None:
+                    self.peer_mem = None
+                if os.environ.get("NXB_HALO_STRICT"):
+                    raise RuntimeError(f"peer-mapped memory unavailable on rank {self.rank}: {err}")
+                transport = "p2p"                   # NCCL / gloo point-to-point: the documented fallback
+        self.transport = transport
+        if self.peer_mem is not None:
+            self._buf = self.peer_mem.buf
+            self._peer_base = self.peer_mem.ptrs
         else:
-            self._buf = torch.zeros(n_state + 64, dtype=torch.float32, device=dev)
+            self._buf = torch.zeros(n_state + MAX_FLAGS, dtype=torch.float32, device=dev)
             self._peer_base = None
         c = self.cap
         self.hw = [(self._buf[0:c], self._buf[c:2 * c]), (self._buf[2 * c:3 * c], self._buf[3 * c:4 * c])]
         self.sed = [torch.zeros(c, dtype=torch.float32, device=dev), torch.zeros(c, dtype=torch.float32, device=dev)]
-        self.flags = self._buf[4 * c:4 * c + 64].view(torch.int32)      # one uint32 per source rank
-        self.ticket = torch.zeros(4 + 256, dtype=torch.int32, device=dev)
+        self.flags = self._buf[4 * c:4 * c + MAX_FLAGS].view(torch.int32)      # one uint32 per source rank
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
         self.cur = 0
         self._pending = False               # a publish has been issued whose incoming flags were not awaited yet
         # concatenated send list, peer after peer
-        self.send_peers = sorted(plan.send_idx)
-        self.recv_peers = sorted(plan.recv_slice)
         if self.send_peers:
             self.send_idx = torch.cat([plan.send_idx[p] for p in self.send_peers]).contiguous()
         else:
@@ -94,11 +184,25 @@ class ShardedErosion:
         self.wait_mode = os.environ.get("NXB_HALO_WAIT", "kernel")
         if self.transport == "fused":
             self._build_send_table()
+            self._peer_arrays = {w: self._peer_ptrs(w) for w in (0, 1)}
         if self.world > 1:
-            dist.barrier(group=group)
+            self._barrier()
+
+    def _barrier(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.peer_mem is not None:
+            self.hw = self.flags = self._buf = None
+            self.peer_mem.close()
+            self.peer_mem = None
 
     def _build_send_table(self):
-        """Per-tile CSR of {dst, vertex-in-tile, peer slot} for the fused sweep (EroSendEntry)."""
+        """Send entries {dst, vertex-in-tile, peer slot} grouped by tile (EroSendEntry); each tile's range
+        of the list goes into its descriptor (send0, send1), from where the producer warp hands it to
+        the consumers with the rest of the stage header."""
         plan, dev = self.plan, self.device
         n_tiles = (plan.n_own + TILE - 1) // TILE
         vs, dsts, slots = [], [], []
@@ -120,23 +224,11 @@ class ShardedErosion:
             self.send_entries = torch.zeros(1, dtype=torch.int64, device=dev)
         ptr = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
         ptr[1:] = torch.cumsum(counts, 0)
-        self.send_ptr = ptr.to(torch.int32).contiguous()
-        self._wait_rank = (C.c_int32 * max(1, len(self.recv_peers)))(*self.recv_peers)
-        # processing order: tiles that read halo slots (a halo segment, or irregular) go last
-        desc = self.tile_plan.mem[: n_tiles * 128].view(torch.int32).view(n_tiles, 32)
-        NSEG = 8                      # nxb_erosion_plan.cuh: seg_start | seg_len | seg_off | nseg | irregular | ...
-        seg_start, nseg, irregular = desc[:, 0:NSEG].to(torch.int64), desc[:, 2 * NSEG:2 * NSEG + 1], desc[:, 2 * NSEG + 1]
-        live = torch.arange(NSEG, device=dev).unsqueeze(0) < nseg
-        needs_halo = ((seg_start >= plan.n_own_pad) & live).any(dim=1) | (irregular != 0)
-        self.tile_order = torch.argsort(needs_halo.to(torch.int8), stable=True).to(torch.int32).contiguous()
-        self.n_halo_tiles = int(needs_halo.sum().item())
-        # boundary set = tiles that send or read halo slots, FIRST (early flag mode)
-        boundary = needs_halo | (counts > 0)
-        self.boundary_order = torch.argsort((~boundary).to(torch.int8), stable=True).to(torch.int32).contiguous()
-        self.n_boundary_tiles = int(boundary.sum().item())
-        self.fused_mode = os.environ.get("NXB_FUSED_MODE", "inkernel" if os.environ.get("NXB_FUSED_INKERNEL_WAIT") else "sepwait")
-        if self.fused_mode == "early" and (self.n_boundary_tiles == 0 or not self.send_peers):
-            self.fused_mode = "sepwait"
+        if n_tiles:
+            desc = self.tile_plan.descriptors()
+            desc[:, rt.ERO_DW_SEND] = ptr[:-1].to(torch.int32)
+            desc[:, rt.ERO_DW_SEND + 1] = ptr[1:].to(torch.int32)
+        self.n_send_tiles = int((counts > 0).sum().item())
 
     # ------------------------------------------------------------------------------------
     def load(self, heights_own):
@@ -150,8 +242,7 @@ class ShardedErosion:
         self.sed[0].zero_(); self.sed[1].zero_()
         self.hw[1 - self.cur][0].zero_(); self.hw[1 - self.cur][1].zero_()
         if self.world > 1:
-            torch.cuda.synchronize() if self.device.type == "cuda" else None
-            dist.barrier(group=self.group)          # nobody still reads / writes the old run's buffers
+            self._barrier()                 # nobody still reads / writes the old run's buffers
         self._publish(self.cur)
 
     def _publish(self, which):
@@ -189,48 +280,56 @@ class ShardedErosion:
                 _ptr_array([self._peer_base[p] + 4 * c * 4 + 4 * self.rank for p in self.send_peers]))
 
     def step(self, rain=RAIN_AMOUNT):
-        src = self.hw[self.cur] + (self.sed[self.cur],)
-        dst = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
-        if self.transport == "fused" and self.world > 1:
-            # one kernel: wait (only where halo data is read) + sweep + put + flag
-            ph, pw, pf = self._peer_ptrs(1 - self.cur)
-            tp = self.tile_plan
-            # The flag wait stays a tiny stream-ordered kernel: waiting INSIDE the sweep (n_wait > 0,
-            # NXB_FUSED_INKERNEL_WAIT=1) works and is bit-identical, but measured bistable on 2 GPUs --
-            # the ranks either stay in lockstep (333 us/sweep) or fall into a wait/compute alternation
-            # (635 us/sweep); see profiles/r01_fused_wait_timeline.txt.
-            n_wait, wait_target, order, n_early = 0, 0, None, 0
-            if self.fused_mode == "early":
-                # boundary tiles first, flags raised as soon as they are done, wait inside the kernel
-                # (the peers' flags of the previous sweep went up a whole interior phase ago)
-                n_wait, wait_target = len(self.recv_peers), self.sweeps + 1
-                order, n_early = rt._ptr(self.boundary_order), self.n_boundary_tiles
-            elif self.fused_mode == "inkernel":
-                n_wait, wait_target = len(self.recv_peers), self.sweeps + 1
-                order = rt._ptr(self.tile_order) if os.environ.get("NXB_FUSED_TILE_ORDER") else None
-            else:
-                self._await()
-            d3 = tp.dist3_for(self.dist)
-            _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
-                      None if d3 is None else rt._ptr(d3), rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
-                      tp.n_own, C.c_float(rain),
-                      rt._ptr(self.send_ptr), rt._ptr(self.send_entries), len(self.send_peers), ph, pw, pf,
-                      rt._ptr(self.flags), self._wait_rank, n_wait,
-                      C.c_uint32(wait_target), C.c_uint32(self.sweeps + 2), self.plan.n_own_pad,
-                      rt._ptr(self.ticket), order, n_early, rt._stream())
-            self._pending = True
-            self.cur = 1 - self.cur
-            self.sweeps += 1
-            return
-        self._await()
-        rt.erode3_step(self.tile_plan, self.dist, src, dst, rain)
-        self.cur = 1 - self.cur
-        self.sweeps += 1
-        self._publish(self.cur)
+        self.run(1, rain)
 
     def run(self, n, rain=RAIN_AMOUNT):
+        """n sweeps.  fused transport: ONE call, the loop (flag wait + sweep-with-exchange per sweep,
+        chained with programmatic dependent launch) is issued from C (nxb_erode3_run_comm_f32)."""
+        if n <= 0:
+            return
+        if self.transport == "fused" and self.world > 1 and self.wait_mode == "kernel":
+            a = self.hw[self.cur] + (self.sed[self.cur],)
+            b = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
+            pa, pb = self._peer_arrays[self.cur], self._peer_arrays[1 - self.cur]
+            tp = self.tile_plan
+            d3 = tp.dist3_for(self.dist)
+            n_wait = len(self.recv_peers)
+            _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
+                      None if d3 is None else rt._ptr(d3),
+                      rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(a[2]), rt._ptr(b[0]), rt._ptr(b[1]), rt._ptr(b[2]),
+                      tp.n_own, C.c_float(rain), int(n),
+                      rt._ptr(self.send_entries), len(self.send_peers), pa[0], pa[1], pb[0], pb[1], pa[2],
+                      rt._ptr(self.flags), rt._ptr(self.recv_ranks), n_wait,
+                      C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream(),
+                      launches=int(n) * (2 if n_wait else 1))
+            self._pending = True
+            if n % 2:
+                self.cur = 1 - self.cur
+            self.sweeps += n
+            return
         for _ in range(n):
-            self.step(rain)
+            src = self.hw[self.cur] + (self.sed[self.cur],)
+            dst = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
+            self._await()
+            if self.transport == "fused" and self.world > 1:
+                pa, pb = self._peer_arrays[self.cur], self._peer_arrays[1 - self.cur]
+                tp = self.tile_plan
+                d3 = tp.dist3_for(self.dist)
+                _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
+                          None if d3 is None else rt._ptr(d3),
+                          rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
+                          tp.n_own, C.c_float(rain), 1,
+                          rt._ptr(self.send_entries), len(self.send_peers), pa[0], pa[1], pb[0], pb[1], pa[2],
+                          rt._ptr(self.flags), rt._ptr(self.recv_ranks), 0,
+                          C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream())
+                self._pending = True
+                self.cur = 1 - self.cur
+                self.sweeps += 1
+                continue
+            rt.erode3_step(self.tile_plan, self.dist, src, dst, rain)
+            self.cur = 1 - self.cur
+            self.sweeps += 1
+            self._publish(self.cur)
 
     def finish(self):
         """Drain: wait for the last incoming halo so buffers may be reused."""
@@ -268,56 +367,109 @@ class ShardedTerrain:
                                     front_cost=float(os.environ.get("NXB_SKELETON_COST", "6")))
         self.begin, self.end = self.ranges[self.rank]
         self.n_own = self.end - self.begin
-        # mesh shard (positions of the own range only)
-        self.xyz, _ = rt.mesh_points(self.k, self.begin, self.end, device=self.device)
-        # neighbour table: every rank builds the whole sorted table, then plans locally (partition.py)
-        cells = rt.mesh_cells(self.k, device=self.device)
-        unsorted = rt.adj_build(cells, self.V)
-        del cells
-        adj_global = rt.adj_sort(unsorted)
-        del unsorted
-        self.plan = build_rank_plan(adj_global, self.rank, self.world, self.ranges)
-        self.dist = rt.icosa_edge_lengths(self.k, adj_global[self.begin:self.end].contiguous(), self.begin, self.end, self.radius)
-        del adj_global
-        torch.cuda.empty_cache()
+        import time
+        t0 = time.perf_counter()
+        # mesh shard: float64 positions of the own range only (closed form)
+        _, self.xyz64 = rt.mesh_points(self.k, self.begin, self.end, f32=False, f64=True, device=self.device)
+        # neighbour rows of the OWN range only, straight from the closed-form triangle generator (no cell
+        # array, no whole-mesh table on any rank); the halo plan comes from one exchange of id lists
+        rows = rt.icosa_adj_rows(self.k, self.begin, self.end, device=self.device)
+        self.plan = build_rank_plan_local(rows, self.rank, self.world, self.ranges, group=group)
+        self.dist = rt.icosa_edge_lengths(self.k, rows, self.begin, self.end, self.radius)
+        del rows
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         self.erosion = ShardedErosion(self.plan, self.dist, transport=transport, group=group)
+        torch.cuda.synchronize()
+        self.setup_ms = {"mesh_rows_plan_edges": (t1 - t0) * 1e3, "tile_plan_peer_memory": (time.perf_counter() - t1) * 1e3}
 
     def fbm(self, out=None, minmax=None):
-        return rt.fbm3(self.tables, self.xyz, self.freq, self.amp, out=out, minmax=minmax)
+        nr = [f / self.radius for f in self.freq]
+        return rt.fbm3_pos64(self.tables, self.xyz64, self.radius, nr, self.amp, out=out, minmax=minmax)
 
     def heights(self, out=None):
         mm = rt.new_minmax(self.device)
         h = self.fbm(out=out, minmax=mm)
         return assemble_heights(h, coll=self.coll, mm=mm)
 
-    def run_from_host(self, points_host, n_sweeps, out_host, world_radius=1.0):
-        """End-to-end step of this rank with HOST buffers: `points_host` float64 [n_own,3] (this rank's
-        slice of the reference's `points`, radius-scaled), `out_host` float64 [n_own] receives the
-        eroded heights.  H2D of the positions and D2H of the result happen here, every call."""
-        xyz = rt.xyz_from_f64(rt.upload(points_host), 1.0 / float(world_radius))
-        mm = rt.new_minmax(self.device)
-        h = rt.fbm3(self.tables, xyz, self.freq, self.amp, minmax=mm)
-        h, _, _ = assemble_heights(h, coll=self.coll, mm=mm)
-        self.erosion.load(h)
-        self.erosion.run(n_sweeps)
-        self.erosion.finish()
-        return rt.download_f64(self.erosion.heights.contiguous(), out=out_host)
-
 
 # ---------------------------------------------------------------------------------------------
+def gather_own(t, ranges, group=None):
+    """Own slices of every rank concatenated in rank order on every rank (all_gather, padded)."""
+    sizes = [e - b for b, e in ranges]
+    m = max(sizes)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    bufs = [torch.empty_like(pad) for _ in sizes]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def sharded_vs_single_gpu_check(terr, seed, n_octaves, sweeps=25):
+    """the sharded pipeline (fBm + assembly + `sweeps` erosion sweeps with the halo
+    exchange) against the SAME work on one GPU (rank 0 runs the whole planet next to its shard), h / w / s
+    compared bit for bit.  Returns the verdict dict on every rank."""
+    import hashlib
+    from .pipeline import TerrainPipeline
+    ero = terr.erosion
+    h, _, lvl = terr.heights()
+    ero.load(h)
+    ero.run(sweeps - 2)
+    ero.step(); ero.step()
+    ero.finish()
+    torch.cuda.synchronize()
+    H = gather_own(ero.heights.contiguous(), terr.ranges, terr.group)
+    W = gather_own(ero.water.contiguous(), terr.ranges, terr.group)
+    S = gather_own(ero.sediment.contiguous(), terr.ranges, terr.group)
+    verdict = torch.zeros(2, dtype=torch.int64, device=terr.device)
+    sha = ""
+    if terr.rank == 0:
+        pipe = TerrainPipeline(terr.k, seed=seed, n_octaves=n_octaves, radius=terr.radius)
+        pipe.build_mesh()
+        h1, _, lvl1 = pipe.heights()
+        st = pipe.erosion_state(h1)
+        st.run(sweeps)
+        torch.cuda.synchronize()
+        same = torch.equal(H, st.heights) and torch.equal(W, st.water) and torch.equal(S, st.sediment) and lvl == lvl1
+        verdict[0] = int(same)
+        verdict[1] = int(torch.isfinite(H).all().item())
+        sha = hashlib.sha1(H.cpu().numpy().tobytes()).hexdigest()
+        del pipe, st, h1
+    del H, W, S
+    torch.cuda.empty_cache()
+    dist.broadcast(verdict, 0, group=terr.group)
+    return {"sweeps": sweeps, "bit_identical": bool(verdict[0].item()), "all_finite": bool(verdict[1].item()),
+            "compared": "heights, water, sediment of all vertices + ocean level vs one GPU (torch.equal)",
+            "sha1_heights": sha, "transport": ero.transport,
+            "peer_memory": ero.peer_mem.kind if ero.peer_mem is not None else None}
+
+
 def run_multi_gpu_bench(args, rank, world, local, emit=None):
     """bench.py --gpus N (N > 1): same step as the single-GPU arm, vertex range sharded over N ranks."""
     import json
     import statistics
     import sys
+    import time
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench as B
+    from . import shard
 
     k, n_oct, iters = args.division, args.octaves, args.iters
     transport = os.environ.get("NXB_HALO", "fused")
+    torch.cuda.synchronize(); dist.barrier()
+    t_setup = time.perf_counter()
     terr = ShardedTerrain(k, seed=args.seed, n_octaves=n_oct, radius=1.0, transport=transport)
+    torch.cuda.synchronize(); dist.barrier()
+    setup_total_ms = (time.perf_counter() - t_setup) * 1e3
+    peak_setup_gib = torch.cuda.max_memory_allocated() / 2 ** 30
     V, n_own = terr.V, terr.n_own
     ero = terr.erosion
+    # ---- correctness first: sharded == one GPU, bit for bit, at THIS size, before anything is timed
+    check = sharded_vs_single_gpu_check(terr, args.seed, n_oct, sweeps=25)
+    if not check["bit_identical"]:
+        if rank == 0:
+            sys.stderr.write(f"mgpu_check FAILED: {json.dumps(check)}\n")
+        raise SystemExit(3)
     h_buf = torch.empty(n_own, dtype=torch.float32, device=terr.device)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -365,27 +517,38 @@ def run_multi_gpu_bench(args, rank, world, local, emit=None):
     dist.all_reduce(halo, op=dist.ReduceOp.MAX)
     nonfinite = torch.tensor([int((~torch.isfinite(ero.heights)).sum().item())], dtype=torch.int64, device=terr.device)
     dist.all_reduce(nonfinite)
-    # ---- end to end with host buffers: every rank uploads its slice of `points`, downloads its heights
+    # the same sweeps on finite data (first 100 sweeps of a run)
+    h_fin, _, _ = terr.heights()
+    fin = []
+    for _ in range(3):
+        ero.load(h_fin)
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = ev(), ev()
+        a.record(); ero.run(100); ero.finish(); b.record()
+        torch.cuda.synchronize()
+        fin.append(a.elapsed_time(b) / 100)
+    fin_t = torch.tensor([min(fin)], dtype=torch.float64, device=terr.device)
+    dist.all_reduce(fin_t, op=dist.ReduceOp.MAX)
+    mem = torch.tensor([peak_setup_gib, torch.cuda.max_memory_allocated() / 2 ** 30], dtype=torch.float64, device=terr.device)
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    tiles = torch.tensor([ero.tile_plan.n_tiles, ero.tile_plan.n_irregular, ero.tile_plan.n_affine, ero.tile_plan.n_affine3],
+                         dtype=torch.int64, device=terr.device)
+    dist.all_reduce(tiles)
+    # ---- end to end through the reference-named numpy API: every rank passes ITS slices of the same
+    # arrays to the same calls (bench.run_e2e, one definition for every N)
     e2e = None
     if not args.no_e2e:
-        import time
         pts = torch.empty((n_own, 3), dtype=torch.float64, pin_memory=True)
-        pts.copy_(rt.mesh_points(k, terr.begin, terr.end, f32=False, f64=True)[1])
-        out_h = torch.empty(n_own, dtype=torch.float64, pin_memory=True)
-        pts_np, out_np = pts.numpy(), out_h.numpy()
-        terr.run_from_host(pts_np, iters, out_np)            # warm-up
-        torch.cuda.synchronize(); dist.barrier()
-        reps = max(1, min(2, args.steps))
-        t_0 = time.perf_counter()
-        for _ in range(reps):
-            terr.run_from_host(pts_np, iters, out_np)
-        torch.cuda.synchronize(); dist.barrier()
-        dt = torch.tensor([(time.perf_counter() - t_0) / reps], dtype=torch.float64, device=terr.device)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": V * (n_oct + iters) / dt.item() / 1e6, "unit": B.UNIT, "ms_per_step": dt.item() * 1e3,
-               "h2d_bytes_per_step": int(V * 24), "d2h_bytes_per_step": int(V * 8),
-               "api": "nixis_b200.multigpu.ShardedTerrain.run_from_host: every rank uploads its float64 slice of "
-                      "`points` from pinned memory and downloads its float64 heights (bytes summed over ranks)"}
+        pts.copy_(terr.xyz64)
+        nbr = torch.empty((n_own, 6), dtype=torch.int32, pin_memory=True)
+        nbr.copy_(rt.icosa_adj_rows(k, terr.begin, terr.end))
+        torch.cuda.synchronize()
+        ero.close()                                   # the API calls build their own plan / peer memory
+        shard.set_shard(terr.ranges)
+        try:
+            e2e = B.run_e2e(args, V, pts.numpy(), nbr.numpy(), terr.perm, terr.pgi, np, torch, sharded=True)
+        finally:
+            shard.clear_shard()
     if rank != 0:
         return
     value = V * (n_oct + iters) / (ms_per_step * 1e-3) / 1e6
@@ -396,15 +559,25 @@ def run_multi_gpu_bench(args, rank, world, local, emit=None):
     line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": B.workload_config(args),
+            "mgpu_check": check,
             "fbm_plus_assembly_ms": fbm_asm_ms,
             "erosion": {"value": V * iters / (ero_ms * 1e-3) / 1e6, "unit": "Mvert-iters/s", "ms": ero_ms,
-                        "halo_transport": transport, "max_halo_vertices_per_rank": int(halo[0].item()),
+                        "halo_transport": ero.transport, "max_halo_vertices_per_rank": int(halo[0].item()),
                         "max_sent_vertices_per_rank_per_sweep": int(halo[1].item()),
-                        "nonfinite_heights_after_last_step": int(nonfinite.item())},
+                        "nonfinite_heights_after_last_step": int(nonfinite.item()),
+                        "finite_data": {"sweeps": 100, "ms_per_sweep": fin_t.item(), "value": V / (fin_t.item() * 1e-3) / 1e6,
+                                        "unit": "Mvert-iters/s"}},
             "roofline": {"kernel": "erode3_plan_kernel (per GPU, incl. halo wait/put per sweep)", "bound": "hbm",
                          "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ero_gbs / hbm_peak,
                          "traffic": None, "peak_source": hbm_src,
-                         "algorithmic_bytes_per_launch": B.BYTES_PER_VERT_ITER * n_own, "avg_launch_ms": ero_launch_ms},
+                         "algorithmic_bytes_per_launch": B.BYTES_PER_VERT_ITER * n_own, "avg_launch_ms": ero_launch_ms,
+                         "tiles_all_ranks": {"total": int(tiles[0]), "irregular": int(tiles[1]), "affine": int(tiles[2]),
+                                             "affine_one_length_per_edge": int(tiles[3])}},
+            "setup_ms": {"total_max_over_ranks_incl_barriers": setup_total_ms, **terr.setup_ms, "in_timed_step": False,
+                         "note": "every rank builds ONLY its own vertex range (positions, neighbour rows from the closed-form "
+                                 "triangle scan, halo plan by id-list exchange, edge lengths, tile plan, peer memory)"},
+            "peak_device_memory_gib": {"after_setup_max_over_ranks": mem[0].item(), "whole_run_max_over_ranks": mem[1].item(),
+                                       "note": "whole_run includes rank 0's single-GPU reference of mgpu_check"},
             "clocks": clocks, "gpu_launches": launches}
     if e2e is not None:
         line["e2e"] = e2e

@@ -7,10 +7,14 @@ The stencil radius is 1 and a sweep reads only the neighbours' height and water
 reference -- its HALO -- and nothing else.
 
 Everything here is integer index logic on tensors (torch ops that run on CPU and on CUDA), done
-once per mesh.  Because every rank holds the full neighbour table while planning, each rank can
-derive every other rank's halo locally: planning needs no communication and is deterministic, so
-the index lists are bit-identical on every rank (tests/test_partition.py checks them against a
-plain-python construction).
+once per mesh.  Two planners produce the same index lists (tests/test_partition.py checks both
+against a plain-python construction):
+  * build_rank_plan        -- from the WHOLE neighbour table (every rank derives every rank's halo
+                              locally, no communication; O(V) memory per rank: small meshes, tests);
+  * build_rank_plan_local  -- from the rank's OWN rows only: each rank finds its halo, asks the
+                              owners for it (one all-gather of counts + one point-to-point exchange
+                              of id lists) and learns from the requests it receives what it must
+                              send.  No rank holds anything of size O(V).
 
 Local numbering of rank r:   [0, n_own)                       own vertices, global id = begin + i
                              [n_own_pad, n_own_pad + n_halo)  halo slots, sorted by global id
@@ -157,3 +161,66 @@ def exchange_halo_torch(plan: RankPlan, arrays, group=None):
             rbuf, off, cnt = item
             for i, a in enumerate(arrays):
                 a[plan.n_own_pad + off: plan.n_own_pad + off + cnt] = rbuf[i]
+
+
+def _p2p_exchange(send: Dict[int, torch.Tensor], recv_counts: Dict[int, int], dtype, device, group=None):
+    """Variable-size point-to-point exchange: send[p] goes to rank p, recv_counts[p] elements come
+    back from rank p.  gloo moves CPU tensors, NCCL device tensors."""
+    import torch.distributed as dist
+    cpu = dist.get_backend(group) == "gloo"
+    ops, keep, out = [], [], {}
+    for p, t in send.items():
+        buf = (t.cpu() if cpu else t).contiguous()
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, p, group=group))
+    for p, cnt in recv_counts.items():
+        buf = torch.empty(cnt, dtype=dtype, device="cpu" if cpu else device)
+        out[p] = buf
+        ops.append(dist.P2POp(dist.irecv, buf, p, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return {p: b.to(device) for p, b in out.items()}
+
+
+def build_rank_plan_local(rows: torch.Tensor, rank: int, world: int, ranges, group=None) -> RankPlan:
+    """rows: int32 [n_own, 6] sorted neighbour rows of THIS rank's range (global ids, -1 pads).
+    Collective over `group`: every rank calls it with its own rows."""
+    import torch.distributed as dist
+    begin, end = ranges[rank]
+    n_own = end - begin
+    assert rows.shape[0] == n_own
+    dev = rows.device
+    n_own_pad = round_up(n_own, TILE)
+    halo = halo_ids(rows, begin, end)
+    n_halo = int(halo.numel())
+    capacity = n_own_pad + round_up(n_halo, TILE)
+    g = rows.to(torch.int64)
+    owned = (g >= begin) & (g < end)
+    slot = torch.searchsorted(halo, g.clamp(min=0)) if n_halo else torch.zeros_like(g)
+    local = torch.where(owned, g - begin, slot + n_own_pad)
+    local = torch.where(g < 0, torch.full_like(g, -1), local).to(torch.int32).contiguous()
+    plan = RankPlan(rank, world, begin, end, n_own, n_own_pad, halo, capacity, local)
+    V = ranges[-1][1]
+    bounds = torch.tensor([b for b, _ in ranges] + [V], dtype=torch.int64, device=dev)
+    cuts = torch.searchsorted(halo, bounds).tolist() if n_halo else [0] * (world + 1)
+    want = [cuts[p + 1] - cuts[p] if p != rank else 0 for p in range(world)]      # ids I need from rank p
+    for p in range(world):
+        if want[p] > 0:
+            plan.recv_slice[p] = (cuts[p], want[p])
+    if world == 1:
+        return plan
+    # who asks whom for how much: counts[q][p] = ids rank q needs from rank p
+    cpu = dist.get_backend(group) == "gloo"
+    mine = torch.tensor(want, dtype=torch.int64, device="cpu" if cpu else dev)
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)
+    counts = torch.stack(allc).cpu()
+    requests = _p2p_exchange({p: halo[cuts[p]:cuts[p + 1]] for p in range(world) if want[p] > 0},
+                             {q: int(counts[q, rank]) for q in range(world) if q != rank and int(counts[q, rank]) > 0},
+                             torch.int64, dev, group)
+    for q, ids in requests.items():
+        plan.send_idx[q] = (ids - begin).to(torch.int32).contiguous()
+        plan.send_dst_offset[q] = int(counts[q, :rank].sum())       # my block inside q's (sorted) halo list
+        plan.peer_n_own_pad[q] = round_up(ranges[q][1] - ranges[q][0], TILE)
+    return plan

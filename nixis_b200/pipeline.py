@@ -36,11 +36,17 @@ class Collective:
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
 
+    def _host_side(self):
+        """gloo moves CPU tensors (CPU tests, several ranks sharing one GPU); NCCL device tensors."""
+        return self.dist.get_backend(self.group) == "gloo"
+
     def minmax(self, mm):
         """mm: float32[2] CUDA tensor (local min, max) -> global (min, max) host floats."""
         if self.dist and self.world > 1:
             lo = mm[0:1].clone()
             hi = mm[1:2].clone()
+            if self._host_side():
+                lo, hi = lo.cpu(), hi.cpu()
             self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
             self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
             return float(lo.item()), float(hi.item())
@@ -50,6 +56,8 @@ class Collective:
     def gather_summaries(self, s):
         """s: float32[4] CUDA tensor -> list of per-rank (has, F, U, M) host tuples, rank order."""
         if self.dist and self.world > 1:
+            if self._host_side():
+                s = s.cpu()
             buf = [torch.empty_like(s) for _ in range(self.world)]
             self.dist.all_gather(buf, s, group=self.group)
             return [b.tolist() for b in buf]
@@ -105,7 +113,8 @@ class TerrainPipeline:
         return self.mesh
 
     def fbm(self, out=None, minmax=None):
-        return rt.fbm3(self.tables, self.mesh.xyz, self.freq, self.amp, out=out, minmax=minmax)
+        nr = [f / self.radius for f in self.freq]                     # terrain.py:43 n_freq / world_radius
+        return rt.fbm3_pos64(self.tables, self.mesh.points64(), self.radius, nr, self.amp, out=out, minmax=minmax)
 
     def heights(self):
         mm = rt.new_minmax(self.device)

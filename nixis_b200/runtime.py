@@ -96,11 +96,25 @@ def octave_schedule(n_octaves, n_init_roughness, n_init_strength, n_roughness, n
 # ---------------------------------------------------------------------------------
 # kernels on torch tensors
 def fbm3(tables, xyz, freq, amp, init=None, out=None, minmax=None):
+    """float4 unit-sphere positions (promoted to float64 inside); freq / amp per octave (unit-sphere terms)."""
     n = xyz.shape[0]
     if out is None:
         out = torch.empty(n, dtype=F32, device=xyz.device)
     _lib.call("nxb_fbm3_f32", C.c_void_p(tables.handle), _ptr(xyz), n, len(freq), _dbl(freq), _dbl(amp),
               _ptr(init), _ptr(out), _ptr(minmax), _stream())
+    return out
+
+
+def fbm3_pos64(tables, verts64, scale, nr, amp, init=None, out=None, minmax=None):
+    """The throughput fBm on the reference's own float64 vertices (device float64 [n,3], times `scale`):
+    lattice coordinate (verts * scale) * nr[o] and the candidate selection in float64 exactly as the
+    reference evaluates them, FP32 contributions; amp[o] in output units."""
+    n = verts64.shape[0]
+    assert verts64.dtype == torch.float64 and verts64.shape[1] == 3
+    if out is None:
+        out = torch.empty(n, dtype=F32, device=verts64.device)
+    _lib.call("nxb_fbm3_pos64_f32", C.c_void_p(tables.handle), _ptr(verts64), C.c_double(scale), n, len(nr),
+              _dbl(nr), _dbl(amp), _ptr(init), _ptr(out), _ptr(minmax), _stream())
     return out
 
 
@@ -245,6 +259,18 @@ def adj_build(cells, V):
     return adj
 
 
+def icosa_adj_rows(k, v_begin, v_end, device=None, with_unsorted=False):
+    """Sorted neighbour rows [v_begin, v_end) of the closed-form icosphere (global ids), built from the
+    triangle generator with 52 B of scratch per ROW -- no cell array, no whole-mesh table."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    n = v_end - v_begin
+    adj = torch.empty((n, 6), dtype=torch.int32, device=device)
+    uns = torch.empty((n, 6), dtype=torch.int32, device=device) if with_unsorted else None
+    ws = torch.empty(max(16, _lib.load().nxb_mesh_icosa_adj_rows_workspace(n)), dtype=torch.uint8, device=device)
+    _lib.call("nxb_mesh_icosa_adj_rows", int(k), int(v_begin), int(v_end), _ptr(adj), _ptr(uns), _ptr(ws), _stream())
+    return (adj, uns) if with_unsorted else adj
+
+
 def adj_sort(adj):
     out = torch.empty_like(adj)
     _lib.call("nxb_adj_sort", _ptr(adj), _ptr(out), adj.shape[0], _stream())
@@ -253,6 +279,7 @@ def adj_sort(adj):
 
 ERO_TILE = 256
 ERO_DESC_BYTES, ERO_DESC_WORDS = 128, 32
+ERO_DW_SEND = 28           # csrc/nxb_erosion_plan.cuh: word index of (send0, send1) in a tile descriptor
 
 
 def round_up(n, m):
@@ -276,8 +303,8 @@ def icosa_edge_lengths(k, adj_rows, v_begin, v_end, radius):
 
 
 class ErosionPlan:
-    """Tile plan (halo segments + 16-bit tile-local adjacency) of an int32 [n_own,6] neighbour table
-    whose indices address buffers of `capacity` elements."""
+    """Tile plan (halo segments, 16-bit tile-local adjacency, implicit-adjacency constants) of an
+    int32 [n_own,6] neighbour table whose indices address buffers of `capacity` elements."""
 
     def __init__(self, adj, capacity=None):
         self.adj = adj
@@ -285,21 +312,25 @@ class ErosionPlan:
         self.capacity = round_up(self.n_own, ERO_TILE) if capacity is None else int(capacity)
         nbytes = _lib.load().nxb_erode_plan_bytes(self.n_own)
         self.mem = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=adj.device)
-        stats = (C.c_int32 * 4)()
+        stats = (C.c_int32 * 8)()
         _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
-        self.n_tiles, self.n_irregular, self.max_halo, self.n_affine = stats[0], stats[1], stats[2], stats[3]
+        self.n_tiles, self.n_irregular, self.max_halo, self.n_affine, self.n_affine3 = (stats[i] for i in range(5))
         self._dist3 = {}
 
+    def descriptors(self):
+        """int32 [n_tiles, 32] view of the tile descriptors (nxb_erosion_plan.cuh EroTileDesc)."""
+        return self.mem[: self.n_tiles * ERO_DESC_BYTES].view(torch.int32).view(self.n_tiles, ERO_DESC_WORDS)
+
     def dist3_for(self, dist):
-        """One-length-per-edge table derived from the full [n,6] table `dist` (built once, cached);
-        None unless NXB_ERO_DIST3=1: the sweep streams the full table by default, which measures
-        faster (590 us vs 715-750 us at d=2500; see the header of csrc/nxb_erosion.cu)."""
-        if os.environ.get("NXB_ERO_DIST3", "0") != "1":
+        """One-length-per-edge table derived from the full [n,6] table `dist` (built once per table,
+        cached).  The sweep reads it on the tiles the plan marks (affine tiles with constant owner
+        rows: 36 B per vertex-sweep instead of 48).  NXB_ERO_DIST3=0 streams the full table everywhere."""
+        if os.environ.get("NXB_ERO_DIST3", "1") != "1" or self.n_affine3 == 0:
             return None
         key = dist.data_ptr()
         if key not in self._dist3:
             d3 = torch.empty(_lib.load().nxb_erode_dist3_floats(self.n_own), dtype=F32, device=dist.device)
-            _lib.call("nxb_erode_dist3_build", _ptr(self.mem), _ptr(self.adj), _ptr(dist), self.n_own, _ptr(d3), _stream())
+            _lib.call("nxb_erode_dist3_build", _ptr(self.adj), _ptr(dist), self.n_own, _ptr(d3), _stream())
             self._dist3 = {key: d3}
         return self._dist3[key]
 
@@ -310,6 +341,16 @@ def erode3_step(plan, dist, src, dst, rain):
     _lib.call("nxb_erode3_plan_step_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist), None if d3 is None else _ptr(d3),
               _ptr(src[0]), _ptr(src[1]), _ptr(src[2]), _ptr(dst[0]), _ptr(dst[1]), _ptr(dst[2]),
               plan.n_own, C.c_float(rain), _stream())
+
+
+def erode3_run(plan, dist, a, b, rain, n_sweeps):
+    """erosion.py:180-184 loop in C: n_sweeps sweeps ping-ponging between the (h, w, s) sets a and b
+    (sweep 0 reads a).  Returns the set that holds the result."""
+    d3 = plan.dist3_for(dist)
+    _lib.call("nxb_erode3_run_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist), None if d3 is None else _ptr(d3),
+              _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(b[0]), _ptr(b[1]), _ptr(b[2]),
+              plan.n_own, C.c_float(rain), int(n_sweeps), _stream(), launches=int(n_sweeps))
+    return a if n_sweeps % 2 == 0 else b
 
 
 def erode1_step(adj, h_in, h_out, v_begin, v_end):

@@ -16,14 +16,32 @@ import numpy as np
 import torch
 
 from . import runtime as rt
-from .util import DeviceMesh, _device_xyz
+from .util import DeviceMesh, _device_xyz          # _device_xyz: float4 positions for the 4-D kernel
+
+
+def _fbm3(verts, tables, nr, amp, init=None, out=None, minmax=None):
+    """The fused fBm kernel on whatever the caller holds.  nr[o] multiplies the vertices AS GIVEN
+    (terrain.py:17 `verts * n_roughness`); numpy / float64 tensors / DeviceMesh go through the
+    float64-position entry point, float4 tensors are promoted inside the kernel."""
+    if isinstance(verts, torch.Tensor) and verts.dtype == torch.float32:
+        assert verts.is_cuda and verts.shape[1] == 4
+        return rt.fbm3(tables, verts, nr, amp, init=init, out=out, minmax=minmax)
+    if isinstance(verts, DeviceMesh):
+        v64, scale = verts.points64(), verts.radius            # nixis.py:249 points *= world_radius
+    elif isinstance(verts, torch.Tensor):
+        assert verts.is_cuda and verts.dtype == torch.float64 and verts.shape[1] == 3
+        v64, scale = verts, 1.0
+    else:
+        v = np.ascontiguousarray(verts, dtype=np.float64)
+        assert v.ndim == 2 and v.shape[1] == 3, "verts must be [V,3]"
+        v64, scale = rt.upload(v), 1.0
+    return rt.fbm3_pos64(tables, v64, scale, nr, amp, init=init, out=out, minmax=minmax)
 
 
 def sample_noise(verts, perm, pgi, n_roughness=1, n_strength=0.2, radius=1):
     """One octave (terrain.py:12-29): ((noise3d(verts*n_roughness)+1)*0.5)*n_strength*radius."""
-    xyz, fscale = _device_xyz(verts, 1.0)
     tables = rt.tables_for(perm, pgi)
-    out = rt.fbm3(tables, xyz, [float(n_roughness) * fscale], [float(n_strength) * float(radius)])
+    out = _fbm3(verts, tables, [float(n_roughness)], [float(n_strength) * float(radius)])
     return out if _is_device(verts) else rt.download_f64(out)
 
 
@@ -35,26 +53,24 @@ def sample_octaves(verts, elevations, perm, pgi, n_octaves=1, n_init_roughness=1
                    n_roughness=2.0, n_persistence=0.5, world_radius=1.0, verbose=True, minmax=None, exact=False):
     """Sample octaves of noise and combine them together (terrain.py:32-59).
 
-    exact=False (default): FP32 throughput kernel, result within 1e-5 of the range of the reference's.
+    exact=False (default): throughput kernel -- float64 lattice coordinates and candidate selection
+    (the reference's own decisions), FP32 contributions: within 1e-5 of the range of the reference's result.
     exact=True: float64 kernel without FMA contraction in the reference's operation order -- the
     result is BIT-IDENTICAL to the reference's for the same float64 vertices (about 4x slower)."""
     t0 = time.perf_counter()
     if exact:
         return _sample_octaves_exact(verts, elevations, perm, pgi, n_octaves, n_init_roughness, n_init_strength,
                                      n_roughness, n_persistence, world_radius)
-    # the kernel works on unit-sphere float positions; nr = freq/world_radius applied to the
-    # radius-scaled verts (terrain.py:17,43) is the same lattice coordinate
-    xyz, fscale = _device_xyz(verts, 1.0 / float(world_radius))
     tables = rt.tables_for(perm, pgi)
     freq, amp = rt.octave_schedule(n_octaves, n_init_roughness, n_init_strength, n_roughness, n_persistence)
-    freq = [f * fscale for f in freq]
     device_io = _is_device(verts)
     init = None
     if elevations is not None:
         init = elevations if isinstance(elevations, torch.Tensor) else rt.upload_f32(elevations)
-    mm = minmax if minmax is not None else rt.new_minmax(xyz.device)
-    out = rt.fbm3(tables, xyz, freq, amp, init=init,
-                  out=init if isinstance(elevations, torch.Tensor) else None, minmax=mm)
+    out_t = init if isinstance(elevations, torch.Tensor) else None
+    mm = minmax if minmax is not None else rt.new_minmax(torch.device("cuda", torch.cuda.current_device()))
+    # terrain.py:43: every octave samples verts * (n_freq / world_radius)
+    out = _fbm3(verts, tables, [f / float(world_radius) for f in freq], amp, init=init, out=out_t, minmax=mm)
     if verbose:
         torch.cuda.synchronize()
         print(f"  Octaves 1..{n_octaves} (fused): {time.perf_counter() - t0:.5f} sec")

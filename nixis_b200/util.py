@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import runtime as rt
+from . import shard
 
 try:                    # inside the reference tree: share the reference's globals (cfg.py:3-14)
     import cfg
@@ -41,6 +42,15 @@ class DeviceMesh:
     @property
     def n_vertices(self):
         return self.xyz.shape[0]
+
+    def points64(self):
+        """float64 [n,3] unit-sphere positions on the device (closed form, generated once and kept):
+        what the fBm kernel reads -- the reference evaluates noise on float64 vertices, and the lattice
+        cell / candidate selection must see the same numbers to make the same decisions."""
+        if getattr(self, "_p64", None) is None:
+            self._p64 = rt.mesh_points(self.k, self.v_begin, self.v_begin + self.n_vertices, f32=False, f64=True,
+                                       device=self.xyz.device)[1]
+        return self._p64
 
     def points_numpy(self):
         """float64 [V,3] radius-scaled positions, like `points` after nixis.py:249."""
@@ -98,7 +108,10 @@ _MODES = {None: 0, "lower": 1, "upper": 2}
 
 
 def rescale(x, lower, upper, mid=None, mode=None, u_min=None, u_max=None):
-    """Re-scale (normalize) an array to a given lower and upper bound (util.py:110-175)."""
+    """Re-scale (normalize) an array to a given lower and upper bound (util.py:110-175).
+    Device arithmetic is FP32: float64 numpy input is rounded to float32 first (min / max and the
+    mapping are then exact for those values); the float64 result agrees with the reference's to 1e-6
+    of the output range."""
     if mode is not None and mid is None:
         print("ERROR: Must supply a middle value to use rescale modes.")
         print("Continuing with unmodified data.")
@@ -107,7 +120,7 @@ def rescale(x, lower, upper, mid=None, mode=None, u_min=None, u_max=None):
         return None          # the reference falls off the end of the function (util.py:161-175)
     dev_io = isinstance(x, torch.Tensor)
     xd = x if dev_io else rt.upload_f32(x)
-    x_min, x_max = rt.minmax(xd).tolist()
+    x_min, x_max = shard.collective().minmax(rt.minmax(xd))      # whole-planet min / max under a shard context
     if u_min is not None and u_min < x_min:
         x_min = u_min
     if u_max is not None and u_max > x_max:
@@ -118,13 +131,18 @@ def rescale(x, lower, upper, mid=None, mode=None, u_min=None, u_max=None):
 
 def power_rescale(x, mask=None, mode=None, power=1.0, verbose=True, shift=0.0):
     """Rescale values using a power function (util.py:178-254).  `shift` (extension, default 0)
-    is subtracted from the result, fusing nixis.py:359."""
+    is subtracted from the result, fusing nixis.py:359.  Device arithmetic is FP32 (float64 numpy input
+    is rounded first; the order-dependent if / elif scan of util.py:203-214 is reproduced exactly on the
+    rounded values)."""
     dev_io = isinstance(x, torch.Tensor)
     xd = x if dev_io else rt.upload_f32(x)
-    x_min, x_max = rt.minmax(xd).tolist()
+    coll = shard.collective()
+    x_min, x_max = coll.minmax(rt.minmax(xd))
     if mode in (0, 1) and mask is not None:
         md = mask if isinstance(mask, torch.Tensor) else rt.upload(np.ascontiguousarray(mask).view(np.uint8))
-        summary = rt.power_summary(xd, md, int(mode)).tolist()
+        # the sequential if / elif scan (util.py:203-214) over the whole planet = the per-shard ordered
+        # summaries combined in rank order
+        summary = rt.combine_power_summaries(coll.gather_summaries(rt.power_summary(xd, md, int(mode))))
         lo, hi = rt.power_bounds(summary, x_min, x_max)
         sel = int(mode)
     else:
@@ -237,41 +255,61 @@ def make_gray_array(width, height, dists, nbrs, colors):
     return rt._to_host(out).astype(orig)
 
 
+def make_rgb_array(width, height, dists, nbrs, colors):
+    """Sample vertices and build an RGB map (util.py:310-341): the same blended value in all three
+    channels, int32 [height, width, 3] cast back to the dtype of `colors`."""
+    gray = make_gray_array(width, height, dists, nbrs, colors)
+    if isinstance(gray, torch.Tensor):
+        return gray.unsqueeze(-1).expand(-1, -1, 3).contiguous()
+    return np.repeat(gray[:, :, None], 3, axis=2)
+
+
+# dtype policy of build_image_data (util.py:394-402, 421-427), as data.  Arrays are pre-scaled to
+# 0..255 (as float64) before blending unless they are uint16 / uint32; the exported pixels are uint8
+# except for uint16 sources, which stay uint16 (a pre-scaled array is float64 by then, and float64 /
+# uint32 are on the reference's narrow-to-uint8 list).
+_KEEP_UNSCALED = {"u2": np.uint16, "u4": np.uint8}      # source kind -> exported dtype; everything else: pre-scale, uint8
+
+
+def _dtype_key(dt):
+    dt = np.dtype(dt)
+    return "b" if dt == np.bool_ else f"{dt.kind}{dt.itemsize}"
+
+
 def build_image_data(colors=None, width=None, height=None):
     """Use the nearest-vertex query results to build the maps for export (util.py:369-429).
-    colors: dict name -> [array, mode].  Width / height default to the shape of cfg.IMG_QUERY_DATA
-    (the reference re-reads options.json, util.py:381-383)."""
+    colors: dict name -> [array, mode] with mode 'gray' / 'rgb'.  Width / height default to the shape
+    of cfg.IMG_QUERY_DATA (the reference re-reads options.json, util.py:381-383)."""
     print("Sampling verts for texture...")
     dists, nbrs = cfg.IMG_QUERY_DATA[0], cfg.IMG_QUERY_DATA[1]
     height = height or dists.shape[0]
     width = width or dists.shape[1]
     if not isinstance(colors, dict):
         print("ERROR: Must pass a dict when saving out texture maps.")
+    d_dev = dists if isinstance(dists, torch.Tensor) else rt.upload(np.ascontiguousarray(dists, dtype=np.float64))
+    i_dev = nbrs if isinstance(nbrs, torch.Tensor) else rt.upload(np.ascontiguousarray(nbrs, dtype=np.int64))
+    d_dev, i_dev = d_dev.reshape(height, width, 3), i_dev.reshape(height, width, 3)
     result = {}
-    for key, container in colors.items():
-        array, mode = container[0], container[1]
-        if array.dtype in ('int8', 'uint8', 'bool_'):
-            colors[key] = [rescale(array.astype(np.float64), 0, 255), mode]
-        elif array.dtype in ('uint16', 'uint32'):
-            pass
-        else:
-            colors[key] = [rescale(array, 0, 255), mode]
-    d_dev = rt.upload(np.ascontiguousarray(dists, dtype=np.float64))
-    i_dev = rt.upload(np.ascontiguousarray(nbrs, dtype=np.int64))
-    for key, container in colors.items():
-        array, mode = container[0], container[1]
+    for key in list(colors):
+        array, mode = colors[key][0], str(colors[key][1]).lower()
+        src = np.asarray(array)
+        kind = _dtype_key(src.dtype)
+        values = src
+        if kind not in _KEEP_UNSCALED:
+            values = rescale(src.astype(np.float64), 0, 255)
         t0 = time.perf_counter()
-        if mode in ('gray', 'GRAY', 'grey', 'GREY'):
-            c64 = rt.upload(np.ascontiguousarray(np.asarray(array).astype(np.float64)))
-            pixels = rt._to_host(rt.idw_gray(d_dev.reshape(height, width, 3), i_dev.reshape(height, width, 3), c64))
-        else:
-            raise NotImplementedError("RGB maps (util.py:310-341) are not part of the export row built so far")
+        if mode not in ("gray", "grey", "rgb"):
+            raise ValueError(f"build_image_data: unknown mode {colors[key][1]!r} for map {key!r}")
+        c64 = rt.upload(np.ascontiguousarray(np.asarray(values).astype(np.float64)))
+        pixels = rt._to_host(rt.idw_gray(d_dev, i_dev, c64))
+        if mode == "rgb":
+            pixels = np.repeat(pixels[:, :, None], 3, axis=2)
         colors[key] = None
         print(f"  {key} pixels built in   {time.perf_counter() - t0 :.5f} sec")
-        if array.dtype in ('float16', 'int32', 'uint32', 'float32', 'int64', 'uint64', 'float64'):
-            result[key] = pixels.astype('uint8')
-        else:
-            result[key] = pixels.astype(array.dtype)
+        # make_gray_array / make_rgb_array cast back to the dtype of the colours they were given
+        # (util.py:341, 367), then the export dtype of the table above applies (util.py:424-427)
+        pixels = pixels.astype(np.asarray(values).dtype)
+        result[key] = pixels.astype(_KEEP_UNSCALED.get(kind, np.uint8))
     return result
 
 

@@ -4,11 +4,14 @@ the golden vectors computed by the reference and against the CPU oracle.
 Integer work (perm tables, cells, adjacency) is bit-exact.  Floating point is FP32 on the GPU
 versus float64 in the reference; tolerances are max-abs-error relative to the value RANGE of the
 reference result and are written next to each assertion:
-    fBm 7/8 octaves   <= 1e-5      (FP32 input rounding alone is ~1e-6)
-    fBm 12 octaves    <= 4e-5
+    fBm 7/8 octaves   <= 1e-5      (asserted at 2e-6 on the large meshes: float64 lattice coordinates and
+                                    candidate selection, FP32 contributions)
+    fBm 12 octaves    <= 2e-5
     height assembly   <= 2e-5      (pow / division in FP32)
     erosion, 1 sweep  <= 1e-5 (h); trajectories N<=50 at R=1, N<=5 at Earth radius <= 1e-4
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -116,7 +119,7 @@ def test_sample_octaves_vs_reference_golden(nx, golden):
         perm, pgi = nx.osi.init(s)
         h = nx.terrain.sample_octaves(pts * R, None, perm, pgi, o, 1.5, 0.4, 2.5, 0.5, R, verbose=False)
         tag = f"k{k}_s{s}_o{o}_{'earth' if R != 1.0 else 'unit'}"
-        tol = 1e-5 if o <= 8 else 4e-5
+        tol = 5e-6                         # 1e-5 (8 octaves), 2e-5 (12); float64 selection leaves FP32 rounding only
         assert h.dtype == np.float64 and relerr(h, g[tag]) <= tol, (tag, relerr(h, g[tag]))
 
 
@@ -170,8 +173,9 @@ def test_fbm_large_mesh_vs_oracle(nx, oracle):
     pts = mesh.points_numpy()
     ref = oracle.sample_octaves(pts, None, perm, pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0)
     err = np.abs(h.cpu().numpy().astype(np.float64) - ref) / (ref.max() - ref.min())
-    assert err.max() <= 2.5e-5, err.max()             # rare candidate-set flips at FP32 ties
-    assert np.quantile(err, 0.9999) <= 1e-5
+    # <= 1e-5 of the range at 8 octaves.  The candidate selection is float64 (the reference's
+    # own decisions), so there are no candidate-set flips: what is left is FP32 rounding of the contributions
+    assert err.max() <= 2e-6, err.max()
     # linearity in the amplitude (exact: powers of two)
     h2 = nx.terrain.sample_octaves(mesh, None, perm, pgi, 8, 1.5, 0.8, 2.5, 0.5, 1.0, verbose=False)
     assert nx.torch.equal(h2, 2 * h)
@@ -389,6 +393,29 @@ def test_erosion1_vs_reference_golden(nx, golden, k, seed, R):
     assert r is h and relerr(h, g[f"{t}_it1_n100"]) <= 1e-5
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 32, 200])
+def test_adjacency_rows_of_a_vertex_range_match_the_whole_table(nx, k):
+    """nxb_mesh_icosa_adj_rows (rows of a vertex range straight from the closed-form triangle generator,
+    what every multi-GPU rank builds for its own range) == the matching rows of build_adjacency /
+    sort_adjacency on the whole cell array, bit for bit, for the whole range and for windows that cut
+    through the skeleton, through face boundaries and through mesh rows."""
+    torch = nx.torch
+    V, T = 10 * k * k + 2, 20 * k * k
+    cells = nx.rt.mesh_cells(k)
+    unsorted = nx.rt.adj_build(cells, V)
+    full = nx.rt.adj_sort(unsorted)
+    skel = 12 + 30 * (k - 1)
+    per_face = (k - 1) * (k - 2) // 2
+    cuts = sorted({0, min(V, 5), min(V, 12), min(V, skel // 2), min(V, skel), min(V, skel + 7), min(V, skel + per_face),
+                   min(V, skel + per_face + per_face // 3), min(V, skel + 7 * per_face - 1), V // 2, V - 1, V})
+    for b, e in [(0, V)] + list(zip(cuts[:-1], cuts[1:])):
+        if e <= b:
+            continue
+        rows, uns = nx.rt.icosa_adj_rows(k, b, e, with_unsorted=True)
+        assert torch.equal(uns, unsorted[b:e]), (k, b, e)
+        assert torch.equal(rows, full[b:e]), (k, b, e)
+
+
 def test_erosion_large_single_step_vs_oracle(nx, oracle):
     """d=320, one sweep from identical FP32-rounded state, device-resident path."""
     k = 320
@@ -408,16 +435,15 @@ def test_erosion_large_single_step_vs_oracle(nx, oracle):
 
 
 # ---------------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize("k", [40, 300, 700])
+@pytest.mark.parametrize("k", [40, 300, 700, 1000])
 def test_erosion_dist3_path_bit_identical_to_full_table(nx, monkeypatch, k):
-    """The sweep that streams one stored length per edge (dist3, 48 B/vertex) gives bit for bit what
-    the sweep streaming the full 6-per-vertex table (60 B/vertex) gives -- same values, same order."""
+    """Affine tiles that read ONE stored length per edge (kind 3: dist3 rows staged next to h / w,
+    36 B/vertex) give bit for bit what the full 6-per-vertex table gives -- same values, same order."""
     torch = nx.torch
     pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
     pipe.build_mesh()
     h, _, _ = pipe.heights()
     out = {}
-    monkeypatch.setenv("NXB_ERO_AFFINE", "0")
     for mode in ("1", "0"):
         monkeypatch.setenv("NXB_ERO_DIST3", mode)
         st = pipe.erosion_state(h.clone())
@@ -427,11 +453,9 @@ def test_erosion_dist3_path_bit_identical_to_full_table(nx, monkeypatch, k):
         assert torch.equal(a, b)
     assert bool(torch.isfinite(out["1"][0]).all())
     plan = pipe._plan
-    d3 = plan.mem[: plan.n_tiles * 128].view(torch.int32).view(-1, 32)[:, 19]
-    irregular = plan.mem[: plan.n_tiles * 128].view(torch.int32).view(-1, 32)[:, 17]
-    fast = int(((d3 & 0xff) == 0).logical_and(irregular == 0).sum())
-    print(f"k={k}: {fast} of {plan.n_tiles} tiles stream dist3")
-    assert k < 300 or fast > 0.5 * plan.n_tiles
+    print(f"k={k}: {plan.n_affine3} of {plan.n_affine} affine tiles ({plan.n_tiles} tiles) read one length per edge")
+    assert plan.n_affine3 <= plan.n_affine
+    assert k < 700 or plan.n_affine3 > 0.9 * plan.n_affine
 
 
 @pytest.mark.parametrize("k", [40, 300, 700, 1000])
@@ -457,8 +481,8 @@ def test_erosion_implicit_adjacency_bit_identical(nx, monkeypatch, k):
 
 def test_erosion_exchange_capable_kernel_matches_plain_on_one_gpu(nx):
     """The COMM instantiation of the sweep kernel (the one every multi-GPU rank runs), driven on one
-    GPU with no peers, gives bit for bit what the single-GPU instantiation gives -- with and without
-    an explicit processing order."""
+    GPU with no peers through the C-side loop, gives bit for bit what the single-GPU instantiation
+    gives; and the C-side loop equals n single-sweep calls (with and without dependent launch)."""
     import ctypes as C
     torch = nx.torch
     from nixis_b200 import _lib
@@ -467,24 +491,31 @@ def test_erosion_exchange_capable_kernel_matches_plain_on_one_gpu(nx):
     pipe.build_mesh()
     h, _, _ = pipe.heights()
     st = pipe.erosion_state(h.clone())
-    st.run(6)
+    for _ in range(7):
+        st.step()
     ref = (st.heights.clone(), st.water.clone(), st.sediment.clone())
+    V = pipe.V
+    for pdl in ("1", "0"):
+        os.environ["NXB_ERO_PDL"] = pdl
+        try:
+            st1 = pipe.erosion_state(h.clone())
+            st1.run(7)
+            for a, b in zip(ref, (st1.heights, st1.water, st1.sediment)):
+                assert torch.equal(a, b)
+        finally:
+            os.environ.pop("NXB_ERO_PDL", None)
     tp = pipe._plan
-    ticket = torch.zeros(4 + 256, dtype=torch.int32, device="cuda")
-    rev = torch.arange(tp.n_tiles - 1, -1, -1, dtype=torch.int32, device="cuda")
-    for order in (None, rev):
-        st2 = pipe.erosion_state(h.clone())
-        src, dst = st2.cur, st2.nxt
-        for _ in range(6):
-            _lib.call("nxb_erode3_plan_step_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st2.dist), None,
-                      rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
-                      tp.n_own, C.c_float(0.3 / 320), None, None, 0, None, None, None, None, None, 0,
-                      C.c_uint32(0), C.c_uint32(0), 0, rt._ptr(ticket), None if order is None else rt._ptr(order), 0, rt._stream())
-            src, dst = dst, src
-        torch.cuda.synchronize()
-        V = pipe.V
-        for a, b in zip(ref, (src[0][:V], src[1][:V], src[2][:V])):
-            assert torch.equal(a, b)
+    ticket = torch.zeros(4, dtype=torch.int32, device="cuda")
+    st2 = pipe.erosion_state(h.clone())
+    a, b = st2.cur, st2.nxt
+    d3 = tp.dist3_for(st2.dist)
+    _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st2.dist), None if d3 is None else rt._ptr(d3),
+              rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(a[2]), rt._ptr(b[0]), rt._ptr(b[1]), rt._ptr(b[2]),
+              tp.n_own, C.c_float(0.3 / 320), 7, None, 0, None, None, None, None, None, None, None, 0,
+              C.c_uint32(0), rt._ptr(ticket), rt._stream())
+    torch.cuda.synchronize()
+    for x, y in zip(ref, (b[0][:V], b[1][:V], b[2][:V])):
+        assert torch.equal(x, y)
 
 
 def test_config2_d1000_fbm_assembly_erosion_vs_oracle(nx, oracle):
@@ -497,7 +528,7 @@ def test_config2_d1000_fbm_assembly_erosion_vs_oracle(nx, oracle):
     ref = oracle.sample_octaves(pts, None, pipe.perm, pipe.pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0)
     h = pipe.fbm()
     err = np.abs(h.cpu().numpy().astype(np.float64) - ref) / (ref.max() - ref.min())
-    assert np.quantile(err, 0.9999) <= 1e-5 and err.max() <= 6e-5, err.max()
+    assert err.max() <= 2e-6, err.max()            # SURVEY 8d allows 1e-5; no candidate-set flips since the selection is float64
     hs, ocean, level = pipe.heights()
     ref_h, ref_ocean, ref_level = oracle.height_assembly(ref)
     assert abs(level - ref_level) < 1e-2
@@ -538,3 +569,91 @@ def test_config3_d2500_full_size_properties(nx):
     # idempotence of the ring sort: sorting a sorted table changes nothing
     again = nx.rt.adj_sort(pipe.adj)
     assert torch.equal(again, pipe.adj)
+
+
+# fBm tolerance at BASELINE sizes: SURVEY 8d asks max |err| / range <= 1e-5; the float64 selection leaves FP32
+# rounding of the contributions only, so the assertion is 5x tighter than the contract
+FBM_TOL_8OCT = 2e-6
+
+
+def test_config3_d2500_oracle_parity(nx, oracle):
+    """BASELINE configs[3] at FULL size against the float64 oracle on the same mesh (the device
+    generator is bit-identical to oracle/icosphere.py, test_mesh_bit_exact_vs_oracle_generator):
+    8-octave fBm, the nixis.py:332-364 assembly chain and 5 erosion_iteration3 sweeps with the
+    SURVEY 8d tolerances, plus the float64 exact mode bit for bit on a 1 M-vertex slice.  The tile
+    planner behaves differently here (80 % affine tiles, 293 irregular) than at d <= 1000."""
+    torch = nx.torch
+    k = 2500
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    pts = pipe.mesh.points_numpy()
+    ref = oracle.sample_octaves(pts, None, pipe.perm, pipe.pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0)
+    h = pipe.fbm()
+    err = np.abs(h.cpu().numpy().astype(np.float64) - ref) / (ref.max() - ref.min())
+    print(f"d=2500 fBm: max err {err.max():.2e}, 99.99 % {np.quantile(err[::16], 0.9999):.2e}")
+    assert err.max() <= FBM_TOL_8OCT, err.max()
+    del err
+    # exact mode: bit-identical on a slice that crosses the skeleton / face-interior boundary
+    lo = 12 + 30 * (k - 1) - 200_000
+    sl = slice(lo, lo + 1_000_000)
+    ex = nx.terrain.sample_octaves(pts[sl], None, pipe.perm, pipe.pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0, verbose=False, exact=True)
+    assert np.array_equal(ex, ref[sl])
+    hs, ocean, level = pipe.heights()
+    ref_h, ref_ocean, ref_level = oracle.height_assembly(ref)
+    del ref
+    assert abs(level - ref_level) < 1e-2
+    flips = ocean.cpu().numpy().view(np.bool_) != ref_ocean
+    assert flips.mean() < 1e-5                      # mask differs only at FP32 distance from the ocean level
+    assert relerr(hs.cpu().numpy()[~flips], ref_h[~flips]) <= 5e-5
+    del ref_h, ref_ocean, flips
+    st = pipe.erosion_state(hs)
+    plan = st.plan
+    print(f"d=2500 plan: {plan.n_tiles} tiles, {plan.n_irregular} irregular, {plan.n_affine} affine, {plan.n_affine3} one-length-per-edge")
+    assert plan.n_affine > 0.7 * plan.n_tiles and plan.n_irregular < 400
+    he = hs.cpu().numpy().astype(np.float64)       # same FP32-rounded start for the oracle
+    st.run(5)
+    adj = pipe.adj.cpu().numpy()
+    wr, sr = oracle.erode_terrain3(pts, adj, he, 5, return_state=True)
+    assert relerr(st.heights.cpu().numpy(), he) <= 1e-4
+    assert relerr(st.water.cpu().numpy(), wr) <= 1e-4
+    assert relerr(st.sediment.cpu().numpy(), sr) <= 1e-4
+
+
+def test_config5_d5000_single_gpu(nx, oracle):
+    """BASELINE configs[4] sizing on ONE GPU (d=5000, 250 000 002 vertices): 12-octave 4-D fBm
+    against the oracle on a strided 2 M-vertex sample, 3 erosion sweeps against the oracle on the
+    FULL mesh, and the HBM-capacity claim of DESIGN.md section 2 as an assertion."""
+    import psutil
+    torch = nx.torch
+    k = 5000
+    torch.cuda.reset_peak_memory_stats()
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=12, radius=1.0)
+    pipe.build_mesh()
+    V = pipe.V
+    assert V == 250_000_002
+    w = [0.5 * f for f in pipe.freq]
+    h4 = nx.rt.fbm4(pipe.tables, pipe.mesh.xyz, pipe.freq, pipe.amp, w)
+    idx = torch.arange(0, V, 125, device="cuda")
+    p64 = nx.rt.mesh_points(k, f32=False, f64=True)[1]
+    sample = p64[idx].cpu().numpy()
+    ref4 = oracle.sample_octaves4(sample, None, pipe.perm, 12, 1.5, 0.4, 2.5, 0.5, 1.0, 0.5)
+    got4 = h4[idx].cpu().numpy().astype(np.float64)
+    err4 = np.abs(got4 - ref4) / (ref4.max() - ref4.min())
+    print(f"d=5000 fBm4 x12 on {len(sample)} sampled vertices: max err {err4.max():.2e}")
+    assert np.quantile(err4, 0.999) <= 2e-5 and err4.max() <= 1e-4, err4.max()
+    hs, _, _ = nx.pipeline.assemble_heights(h4)
+    st = pipe.erosion_state(hs)
+    peak_gib = torch.cuda.max_memory_allocated() / 2 ** 30
+    print(f"d=5000 peak device memory incl. transient setup {peak_gib:.1f} GiB; plan {st.plan.n_tiles} tiles, "
+          f"{st.plan.n_irregular} irregular, {st.plan.n_affine} affine")
+    assert peak_gib < 80.0                          # DESIGN.md section 2: resident + transient fits one B200 twice over
+    h0 = hs.cpu().numpy().astype(np.float64)
+    st.run(3)
+    assert bool(torch.isfinite(st.heights).all())
+    if psutil.virtual_memory().available < 40 * 2 ** 30:
+        pytest.skip("host has too little RAM for the full-mesh oracle sweep at d=5000")
+    pts = p64.cpu().numpy()
+    del p64
+    adj = pipe.adj.cpu().numpy()
+    oracle.erode_terrain3(pts, adj, h0, 3)
+    assert relerr(st.heights.cpu().numpy(), h0) <= 1e-4

@@ -127,6 +127,37 @@ def test_sharded_erosion_bit_identical_gloo(world, oracle):
         assert np.array_equal(hh, h[b:e]) and np.array_equal(ww, wat[b:e]) and np.array_equal(ss, sed[b:e])
 
 
+def _local_plan_worker(rank, world, port, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pts, adj = _mesh(k)
+        V = len(adj)
+        ranges = P.vertex_ranges(V, world, front=12 + 30 * (k - 1), front_cost=6.0)
+        b, e = ranges[rank]
+        ref = P.build_rank_plan(torch.from_numpy(adj), rank, world, ranges)
+        got = P.build_rank_plan_local(torch.from_numpy(adj[b:e].copy()), rank, world, ranges)
+        same = (torch.equal(ref.halo, got.halo) and ref.capacity == got.capacity and torch.equal(ref.local_adj, got.local_adj)
+                and ref.recv_slice == got.recv_slice and ref.send_dst_offset == got.send_dst_offset
+                and ref.peer_n_own_pad == got.peer_n_own_pad and sorted(ref.send_idx) == sorted(got.send_idx)
+                and all(torch.equal(ref.send_idx[p], got.send_idx[p]) for p in ref.send_idx))
+        out[rank] = bool(same)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,world", [(10, 2), (20, 3), (24, 4)])
+def test_local_planner_matches_global_planner_gloo(k, world):
+    """build_rank_plan_local (own rows + a request exchange, no O(V) table on any rank) produces exactly
+    the index lists of build_rank_plan (whole table on every rank)."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_local_plan_worker, args=(world, port, k, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
+
+
 @pytest.mark.parametrize("V,world,front,cost", [(62500002, 8, 74982, 6.0), (10000002, 4, 29982, 6.0), (1024002, 3, 9582, 1.0),
                                                 (162, 4, 42, 6.0), (12, 3, 12, 6.0)])
 def test_vertex_ranges_cost_weighted(V, world, front, cost):
