@@ -216,34 +216,35 @@ int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, vo
 int64_t nxb_erode_dist3_floats(int64_t n_own);
 int nxb_erode_dist3_build(const int32_t *adj, const float *dist, int64_t n_own, float *dist3, void *stream);
 /* erosion.py:197-279 erosion_iteration3 for vertices [0, n_own), FP32 state, ping-pong buffers
- * (reads *_in, writes *_out; no copy-back pass).  `rain` is added to every water value read
- * (erosion.py:182-183 `water += rain_amount` fused).  dist: float[round_up(n_own,256)*6]. */
+ * (reads *_in, writes *_out; no copy-back pass).  Heights and water live INTERLEAVED, hw = float[capacity][2]
+ * = {height, water} per vertex: a neighbour's height and water are always read together, so a run of
+ * neighbours is one bulk copy and a boundary value is one 8-byte peer store; sediment is a separate
+ * float[capacity].  `rain` is added to every water value read (erosion.py:182-183 `water += rain_amount`
+ * fused).  dist: float[round_up(n_own,256)*6]. */
 int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                             const float *h_in, const float *w_in, const float *s_in,
-                             float *h_out, float *w_out, float *s_out,
+                             const float *hw_in, const float *s_in, float *hw_out, float *s_out,
                              int64_t n_own, float rain, void *stream);
 /* erosion.py:180-184: the erode_terrain3 loop, n_sweeps sweeps issued from C (one launch each, chained
  * with programmatic dependent launch).  Sweep 0 reads buffer set A and writes B, sweep 1 reads B ...:
  * the result is in A when n_sweeps is even, in B when it is odd. */
 int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                       float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                       float *hw_a, float *s_a, float *hw_b, float *s_b,
                        int64_t n_own, float rain, int64_t n_sweeps, void *stream);
 /* The same loop on one shard of a multi-GPU run, each sweep fused with the halo exchange in ONE
- * kernel: boundary results are stored straight into the peers' halo slots over NVLink as they are
- * computed and the last CTA raises this rank's flag in every peer; a one-warp kernel in front of
- * each sweep waits for the peers' flags of the previous one.  The plan's tile descriptors carry each
+ * kernel: boundary {height, water} pairs are stored straight into the peers' halo slots over NVLink as
+ * they are computed and the last CTA raises this rank's flag in every peer; a one-warp kernel in front
+ * of each sweep waits for the peers' flags of the previous one.  The plan's tile descriptors carry each
  * tile's range of send_entries (device array of {int32 dst, uint16 vertex-in-tile, uint16 peer slot});
- * peer_h_a/.. : HOST arrays of n_send_peers NVLink-mapped pointers to the peers' buffer sets A and B
- * and to their flag slot for this rank; flags: this rank's uint32 flag array; wait_ranks_dev: device
- * int32[n_wait] source ranks.  Sweep i waits for flag value sweep_base + 1 + i and raises
- * sweep_base + 2 + i (the halo of the initial state is published with value sweep_base + 1, e.g. by
- * nxb_halo_put_f32).  ticket: device uint32, zero. */
+ * peer_hw_a / peer_hw_b: HOST arrays of n_send_peers peer-mapped pointers to the peers' hw buffers of
+ * sets A and B, peer_flag: to their flag slot for this rank; flags: this rank's uint32 flag array;
+ * wait_ranks_dev: device int32[n_wait] source ranks.  Sweep i waits for flag value sweep_base + 1 + i and
+ * raises sweep_base + 2 + i (the halo of the initial state is published with value sweep_base + 1, e.g.
+ * by nxb_halo_put_f32).  ticket: device uint32, zero. */
 int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                            float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                            float *hw_a, float *s_a, float *hw_b, float *s_b,
                             int64_t n_own, float rain, int64_t n_sweeps,
                             const void *send_entries, int n_send_peers,
-                            void *const *peer_h_a, void *const *peer_w_a,
-                            void *const *peer_h_b, void *const *peer_w_b, void *const *peer_flag,
+                            void *const *peer_hw_a, void *const *peer_hw_b, void *const *peer_flag,
                             const void *flags, const int32_t *wait_ranks_dev, int n_wait,
                             uint32_t sweep_base, void *ticket, void *stream);
 /* Reference-exact mode of the sweep: float64 positions / state, no FMA, the reference's operation and
@@ -256,13 +257,13 @@ int nxb_erode3_step_f64(const double *nodes, const int32_t *adj,
 int nxb_erode1_step_f32(const int32_t *adj, const float *h_in, float *h_out,
                         int64_t v_begin, int64_t v_end, void *stream);
 /* ---- multi-GPU halo exchange over NVLink peer memory (csrc/nxb_halo.cu) ------------------------
- * After a sweep, store this rank's boundary h / w values straight into every peer's halo slots
- * (peer_h[p] / peer_w[p] are the peer's state buffers mapped into this process, e.g. by
- * torch.distributed._symmetric_memory) and raise flag_value in the peer's flag slot for this rank.
- * send_idx: concatenated LOCAL indices, peer after peer (src_begin / count per peer); dst_off[p] =
- * first element of peer p's buffer this rank fills.  ticket: device uint32, zero.  One fused kernel. */
-int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send_idx, int npeers,
-                     void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+ * Store this rank's boundary {height, water} pairs straight into every peer's halo slots (peer_hw[p] is
+ * the peer's hw buffer mapped into this process, by torch.distributed._symmetric_memory or nxb_peer_*)
+ * and raise flag_value in the peer's flag slot for this rank.  send_idx: concatenated LOCAL indices,
+ * peer after peer (src_begin / count per peer); dst_off[p] = first element of peer p's buffer this rank
+ * fills.  ticket: device uint32, zero.  One fused kernel; publishes the initial state of a run. */
+int nxb_halo_put_f32(const float *hw, const int32_t *send_idx, int npeers,
+                     void *const *peer_hw, void *const *peer_flag,
                      const int64_t *dst_off, const int64_t *src_begin, const int64_t *count,
                      uint32_t flag_value, void *ticket, void *stream);
 /* Stream-ordered wait until flags[src_ranks[i]] >= target for all i (flags: this rank's uint32 array,

@@ -60,13 +60,13 @@ SIGNATURES = {
     "nxb_erode_plan_build": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "nxb_erode_dist3_floats": (_i64, [_i64]),
     "nxb_erode_dist3_build": (_i, [_p, _p, _i64, _p, _p]),
-    "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
-    "nxb_erode3_run_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64, _p]),
-    "nxb_erode3_run_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64,
-                                     _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, C.c_uint32, _p, _p]),
+    "nxb_erode3_plan_step_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _p]),
+    "nxb_erode3_run_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64, _p]),
+    "nxb_erode3_run_comm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _i64,
+                                     _p, _i, _p, _p, _p, _p, _p, _i, C.c_uint32, _p, _p]),
     "nxb_erode3_step_f64": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _d, _p]),
     "nxb_erode1_step_f32": (_i, [_p, _p, _p, _i64, _i64, _p]),
-    "nxb_halo_put_f32": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
+    "nxb_halo_put_f32": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, C.c_uint32, _p, _p]),
     "nxb_halo_wait": (_i, [_p, _p, _i, C.c_uint32, _p]),
     "nxb_halo_wait_stream": (_i, [_p, _p, _i, C.c_uint32, _p]),
     "nxb_peer_alloc": (_i, [_i64, C.POINTER(_p), _p]),

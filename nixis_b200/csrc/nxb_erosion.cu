@@ -48,15 +48,14 @@
 static_assert(ERO_DIST_FLOATS >= ERO_TILE * 6, "the dist area holds either full rows of the tile or staged dist3 rows");
 
 struct __align__(128) EroStage {
-    float h[ERO_STAGE_ELEMS];           // kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
-    float w[ERO_STAGE_ELEMS];
+    float2 hw[ERO_STAGE_ELEMS];         // {height, water}; kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
     float s[ERO_TILE];
     float dist[ERO_DIST_FLOATS];        // kinds 1/2: [256][6] full rows; kind 3: dist3 rows [window 264 | leading halo slots][3]
     uint16_t adj[ERO_TILE * 6];         // kind 1 only
     // header, written by producer lane 0 before it arms the full barrier
     int32_t kind, irregular, tile, pad0;
     int32_t send0, send1, pad1, pad2;   // this tile's range of the send-entry list (multi-GPU)
-    int32_t affk4[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &h[c] / &w[c]
+    int32_t affk8[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]
     int32_t d3k4[8];                    // kind 3: byte offset of slot q's edge length relative to &dist[3 c]
 };
 
@@ -70,14 +69,14 @@ struct __align__(128) EroStage {
 struct EroSendEntry { int32_t dst; uint16_t c; uint16_t peer; };
 
 // Fused halo exchange (multi-GPU shards; all pointers null / counts zero on a single GPU):
-//   * consumers store the freshly computed h / w of boundary vertices straight into the peers'
+//   * consumers store the freshly computed {h, w} pair of boundary vertices straight into the peers'
 //     halo slots (NVLink-mapped peer memory) right after computing them;
 //   * the last CTA to finish raises this rank's flag in every peer (after system-scope fences);
 //   * the peers' flags of the previous sweep are awaited by a one-warp kernel in front of the
 //     sweep (nxb_halo.cu), overlapped with this kernel's prologue by programmatic dependent launch.
 struct EroComm {
     const EroSendEntry *send_entries;
-    float *peer_h[ERO_MAX_PEERS], *peer_w[ERO_MAX_PEERS];   // peers' OUTPUT buffers of this sweep
+    float2 *peer_hw[ERO_MAX_PEERS];     // peers' OUTPUT {height, water} buffer of this sweep
     uint32_t *peer_flag[ERO_MAX_PEERS]; // peers' flag slot for this rank
     int n_send_peers;
     uint32_t flag_value;
@@ -91,8 +90,10 @@ struct EroPlanArgs {
     const float *dist3;                                 // one entry per edge [.][3] (null: full table only)
     int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
-    const float *h_in, *w_in, *s_in;
-    float *h_out, *w_out, *s_out;
+    const float2 *hw_in;                                // {height, water} interleaved: ONE bulk copy per run
+    const float *s_in;
+    float2 *hw_out;
+    float *s_out;
     int64_t n_own;
     float rain;
     EroComm comm;
@@ -133,6 +134,10 @@ __device__ __forceinline__ float lds_f32_at(const char *base, int byte_off)
 {
     return *reinterpret_cast<const float *>(base + byte_off);
 }
+__device__ __forceinline__ float2 lds_f32x2_at(const char *base, int byte_off)
+{
+    return *reinterpret_cast<const float2 *>(base + byte_off);
+}
 
 // COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop
 // (the sweep is issue-co-limited: each instruction per vertex counts).
@@ -144,7 +149,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     EroStage *stage = reinterpret_cast<EroStage *>(smem_raw);
     __shared__ __align__(8) uint64_t full[ERO_STAGES_MAX], empty[ERO_STAGES_MAX];
     const int n_stages = a.n_stages;
-    __shared__ float send_h[COMM ? ERO_TILE : 1], send_w[COMM ? ERO_TILE : 1];
+    __shared__ float2 send_hw[COMM ? ERO_TILE : 1];
     __shared__ bool s_last;
     bool cta_sent = false;
 
@@ -206,9 +211,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             if (kind != ERO_KIND_CODES) {
                 // window layout: [v0 - 4, v0 + 260) of h and w, halo runs behind it; no adjacency codes
                 if (lane == 0) {
-                    st.affk4[0] = (int)(int16_t)(kw0 & 0xffff) * 4; st.affk4[1] = (kw0 >> 16) * 4;
-                    st.affk4[2] = (int)(int16_t)(kw1 & 0xffff) * 4; st.affk4[3] = (kw1 >> 16) * 4;
-                    st.affk4[4] = (int)(int16_t)(kw2 & 0xffff) * 4; st.affk4[5] = (kw2 >> 16) * 4;
+                    st.affk8[0] = (int)(int16_t)(kw0 & 0xffff) * 8; st.affk8[1] = (kw0 >> 16) * 8;
+                    st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
+                    st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
                     uint32_t tx = (uint32_t)(ERO_WIN * 8 + ERO_TILE * 4) + (uint32_t)halo_used * 8u;
                     if (kind == ERO_KIND_AFFINE3) {
                         st.d3k4[0] = (int)(int16_t)(dk0 & 0xffff) * 4; st.d3k4[1] = (dk0 >> 16) * 4;
@@ -219,14 +224,12 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                         tx += (uint32_t)(ERO_TILE * 24);
                     }
                     nxb_mbar_expect_tx(&full[s], tx);
-                    nxb_bulk_g2s(st.h, a.h_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
-                    nxb_bulk_g2s(st.w, a.w_in + v0 - ERO_WIN_PAD, ERO_WIN * 4, &full[s]);
+                    nxb_bulk_g2s(st.hw, a.hw_in + v0 - ERO_WIN_PAD, ERO_WIN * 8, &full[s]);
                     nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
                     if (kind == ERO_KIND_AFFINE3) nxb_bulk_g2s(st.dist, a.dist3 + (v0 - ERO_WIN_PAD) * 3, ERO_WIN * 12, &full[s]);
                     else                          nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 } else if (q < nseg) {
-                    nxb_bulk_g2s(st.h + ERO_WIN + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
-                    nxb_bulk_g2s(st.w + ERO_WIN + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+                    nxb_bulk_g2s(st.hw + ERO_WIN + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
                     if (seg_off < d3_rows) {
                         // dist3 rows of the (smaller-numbered) vertices of this run: owners of the backward edges
                         const uint32_t n3 = min(seg_len, d3_rows - seg_off);
@@ -236,14 +239,12 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             } else if (lane == 0) {
                 const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
                 nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
-                nxb_bulk_g2s(st.h, a.h_in + v0, ERO_TILE * 4, &full[s]);
-                nxb_bulk_g2s(st.w, a.w_in + v0, ERO_TILE * 4, &full[s]);
+                nxb_bulk_g2s(st.hw, a.hw_in + v0, ERO_TILE * 8, &full[s]);
                 nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
                 nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 nxb_bulk_g2s(st.adj, a.adj16 + v0 * 6, ERO_TILE * 12, &full[s]);
             } else if (q < nseg && !irregular) {
-                nxb_bulk_g2s(st.h + ERO_TILE + seg_off, a.h_in + seg_start, seg_len * 4u, &full[s]);
-                nxb_bulk_g2s(st.w + ERO_TILE + seg_off, a.w_in + seg_start, seg_len * 4u, &full[s]);
+                nxb_bulk_g2s(st.hw + ERO_TILE + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
             }
             __syncwarp();
             if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
@@ -269,16 +270,15 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             float me, wo, so;
             if (kind != ERO_KIND_CODES) {
                 // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
-                const char *hb = reinterpret_cast<const char *>(st.h + c), *wb = reinterpret_cast<const char *>(st.w + c);
-                me = st.h[c + ERO_WIN_PAD]; wo = st.w[c + ERO_WIN_PAD]; so = st.s[c];
-                const int4 ka = *reinterpret_cast<const int4 *>(st.affk4);
-                const int2 kb = *reinterpret_cast<const int2 *>(st.affk4 + 4);
-                hn[0] = lds_f32_at(hb, ka.x); wn[0] = lds_f32_at(wb, ka.x);
-                hn[1] = lds_f32_at(hb, ka.y); wn[1] = lds_f32_at(wb, ka.y);
-                hn[2] = lds_f32_at(hb, ka.z); wn[2] = lds_f32_at(wb, ka.z);
-                hn[3] = lds_f32_at(hb, ka.w); wn[3] = lds_f32_at(wb, ka.w);
-                hn[4] = lds_f32_at(hb, kb.x); wn[4] = lds_f32_at(wb, kb.x);
-                hn[5] = lds_f32_at(hb, kb.y); wn[5] = lds_f32_at(wb, kb.y);
+                const char *hwb = reinterpret_cast<const char *>(st.hw + c);
+                const float2 own = st.hw[c + ERO_WIN_PAD];
+                me = own.x; wo = own.y; so = st.s[c];
+                const int4 ka = *reinterpret_cast<const int4 *>(st.affk8);
+                const int2 kb = *reinterpret_cast<const int2 *>(st.affk8 + 4);
+                const float2 n0 = lds_f32x2_at(hwb, ka.x), n1 = lds_f32x2_at(hwb, ka.y), n2 = lds_f32x2_at(hwb, ka.z),
+                             n3 = lds_f32x2_at(hwb, ka.w), n4 = lds_f32x2_at(hwb, kb.x), n5 = lds_f32x2_at(hwb, kb.y);
+                hn[0] = n0.x; wn[0] = n0.y; hn[1] = n1.x; wn[1] = n1.y; hn[2] = n2.x; wn[2] = n2.y;
+                hn[3] = n3.x; wn[3] = n3.y; hn[4] = n4.x; wn[4] = n4.y; hn[5] = n5.x; wn[5] = n5.y;
                 if (kind == ERO_KIND_AFFINE3) {
                     // one stored length per edge: own dist3 row (forward slots) or the neighbour's row
                     // (backward slots), entry and row distance constant over the tile
@@ -293,7 +293,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
                 }
             } else {
-                me = st.h[c]; wo = st.w[c]; so = st.s[c];
+                const float2 own = st.hw[c];
+                me = own.x; wo = own.y; so = st.s[c];
                 const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
                 const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
                 d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
@@ -302,7 +303,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
                     const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) { hn[q] = st.h[code[q] & ERO_CODE_POS]; wn[q] = st.w[code[q] & ERO_CODE_POS]; }
+                    for (int q = 0; q < 6; ++q) { const float2 nq = st.hw[code[q] & ERO_CODE_POS]; hn[q] = nq.x; wn[q] = nq.y; }
                 } else {
                     // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
                     const int64_t vv = v < a.n_own ? v : a.n_own - 1;
@@ -312,7 +313,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
                         const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
-                        hn[q] = __ldg(a.h_in + n); wn[q] = __ldg(a.w_in + n);
+                        const float2 nq = __ldg(a.hw_in + n);
+                        hn[q] = nq.x; wn[q] = nq.y;
                     }
                 }
             }
@@ -320,14 +322,13 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
             float hh, ww, ss;
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
-            if (v < a.n_own) { a.h_out[v] = hh; a.w_out[v] = ww; a.s_out[v] = ss; }
+            if (v < a.n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
             if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
-                send_h[c] = hh; send_w[c] = ww;
+                send_hw[c] = make_float2(hh, ww);
                 asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
                 for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
                     const EroSendEntry en = a.comm.send_entries[e];
-                    a.comm.peer_h[en.peer][en.dst] = send_h[en.c];
-                    a.comm.peer_w[en.peer][en.dst] = send_w[en.c];
+                    a.comm.peer_hw[en.peer][en.dst] = send_hw[en.c];      // one 8-byte store over NVLink
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
                 cta_sent = true;
@@ -656,21 +657,20 @@ static int ero_base_args(EroPlanArgs &a, const EroLaunchCfg &cfg, const void *pl
     return NXB_OK;
 }
 
-static int ero_set_buffers(EroPlanArgs &a, const float *h_in, const float *w_in, const float *s_in,
-                           float *h_out, float *w_out, float *s_out)
+static int ero_set_buffers(EroPlanArgs &a, const float *hw_in, const float *s_in, float *hw_out, float *s_out)
 {
-    NXB_ARG(h_in && w_in && s_in && h_out && w_out && s_out);
-    NXB_ARG(h_in != h_out && w_in != w_out && s_in != s_out);
-    NXB_ARG((((uintptr_t)h_in | (uintptr_t)w_in | (uintptr_t)s_in) & 15) == 0);
-    a.h_in = h_in; a.w_in = w_in; a.s_in = s_in;
-    a.h_out = h_out; a.w_out = w_out; a.s_out = s_out;
+    NXB_ARG(hw_in && s_in && hw_out && s_out);
+    NXB_ARG(hw_in != hw_out && s_in != s_out);
+    NXB_ARG((((uintptr_t)hw_in | (uintptr_t)s_in | (uintptr_t)hw_out) & 15) == 0);
+    a.hw_in = (const float2 *)hw_in; a.s_in = s_in;
+    a.hw_out = (float2 *)hw_out; a.s_out = s_out;
     return NXB_OK;
 }
 
 // n_sweeps sweeps, ping-pong between buffer sets A and B (sweep 0 reads A): the result is in A when
-// n_sweeps is even, in B when it is odd.
+// n_sweeps is even, in B when it is odd.  hw_*: {height, water} interleaved, float[capacity][2].
 NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                               float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                               float *hw_a, float *s_a, float *hw_b, float *s_b,
                                int64_t n_own, float rain, int64_t n_sweeps, void *stream)
 {
     NXB_ARG(n_own >= 0 && n_sweeps >= 0);
@@ -681,7 +681,7 @@ NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const f
     EroPlanArgs a;
     if ((rc = ero_base_args(a, cfg, plan_mem, adj, dist, dist3, n_own, rain))) return rc;
     for (int64_t i = 0; i < n_sweeps; ++i) {
-        rc = (i & 1) ? ero_set_buffers(a, h_b, w_b, s_b, h_a, w_a, s_a) : ero_set_buffers(a, h_a, w_a, s_a, h_b, w_b, s_b);
+        rc = (i & 1) ? ero_set_buffers(a, hw_b, s_b, hw_a, s_a) : ero_set_buffers(a, hw_a, s_a, hw_b, s_b);
         if (rc) return rc;
         if ((rc = ero_launch<false>(cfg, a, (cudaStream_t)stream))) return rc;
     }
@@ -689,12 +689,10 @@ NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const f
 }
 
 NXB_API int nxb_erode3_plan_step_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                                     const float *h_in, const float *w_in, const float *s_in,
-                                     float *h_out, float *w_out, float *s_out,
+                                     const float *hw_in, const float *s_in, float *hw_out, float *s_out,
                                      int64_t n_own, float rain, void *stream)
 {
-    return nxb_erode3_run_f32(plan_mem, adj, dist, dist3, (float *)h_in, (float *)w_in, (float *)s_in,
-                              h_out, w_out, s_out, n_own, rain, 1, stream);
+    return nxb_erode3_run_f32(plan_mem, adj, dist, dist3, (float *)hw_in, (float *)s_in, hw_out, s_out, n_own, rain, 1, stream);
 }
 
 int nxb_halo_wait_launch(const void *flags, const int32_t *src_ranks, int npeers, uint32_t target, int pdl, cudaStream_t st);
@@ -704,17 +702,16 @@ int nxb_halo_wait_launch(const void *flags, const int32_t *src_ranks, int npeers
 // even; it stores boundary results into the peers' OTHER set (peer_h_b / peer_w_b when i is even),
 // waits for flag value sweep_base + 1 + i and raises sweep_base + 2 + i.
 NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
-                                    float *h_a, float *w_a, float *s_a, float *h_b, float *w_b, float *s_b,
+                                    float *hw_a, float *s_a, float *hw_b, float *s_b,
                                     int64_t n_own, float rain, int64_t n_sweeps,
                                     const void *send_entries, int n_send_peers,
-                                    void *const *peer_h_a, void *const *peer_w_a,
-                                    void *const *peer_h_b, void *const *peer_w_b, void *const *peer_flag,
+                                    void *const *peer_hw_a, void *const *peer_hw_b, void *const *peer_flag,
                                     const void *flags, const int32_t *wait_ranks_dev, int n_wait,
                                     uint32_t sweep_base, void *ticket, void *stream)
 {
     NXB_ARG(n_own >= 0 && n_sweeps >= 0);
     NXB_ARG(n_send_peers >= 0 && n_send_peers <= ERO_MAX_PEERS && n_wait >= 0 && n_wait <= 32);
-    NXB_ARG(n_send_peers == 0 || (send_entries && peer_h_a && peer_w_a && peer_h_b && peer_w_b && peer_flag && ticket));
+    NXB_ARG(n_send_peers == 0 || (send_entries && peer_hw_a && peer_hw_b && peer_flag && ticket));
     NXB_ARG(n_wait == 0 || (flags && wait_ranks_dev));
     if (n_sweeps == 0) return NXB_OK;
     EroLaunchCfg cfg;
@@ -726,14 +723,13 @@ NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, co
         if (n_wait > 0 && (rc = nxb_halo_wait_launch(flags, wait_ranks_dev, n_wait, sweep_base + 1u + (uint32_t)i, cfg.pdl, (cudaStream_t)stream))) return rc;
         if (n_own == 0) continue;
         const bool odd = (i & 1) != 0;
-        rc = odd ? ero_set_buffers(a, h_b, w_b, s_b, h_a, w_a, s_a) : ero_set_buffers(a, h_a, w_a, s_a, h_b, w_b, s_b);
+        rc = odd ? ero_set_buffers(a, hw_b, s_b, hw_a, s_a) : ero_set_buffers(a, hw_a, s_a, hw_b, s_b);
         if (rc) return rc;
         memset(&a.comm, 0, sizeof a.comm);
         if (n_send_peers > 0) {
             a.comm.send_entries = (const EroSendEntry *)send_entries;
             for (int p = 0; p < n_send_peers; ++p) {
-                a.comm.peer_h[p] = (float *)(odd ? peer_h_a[p] : peer_h_b[p]);
-                a.comm.peer_w[p] = (float *)(odd ? peer_w_a[p] : peer_w_b[p]);
+                a.comm.peer_hw[p] = (float2 *)(odd ? peer_hw_a[p] : peer_hw_b[p]);
                 a.comm.peer_flag[p] = (uint32_t *)peer_flag[p];
             }
             a.comm.n_send_peers = n_send_peers;

@@ -17,7 +17,7 @@
 #define HALO_MAX_PEERS 8
 
 struct HaloPeer {
-    float *h, *w;               // peer's destination buffers (NVLink-mapped), already offset to its halo area
+    float2 *hw;                 // peer's destination {height, water} buffer (peer-mapped)
     uint32_t *flag;             // peer's flag slot for THIS rank
     int64_t dst_off;            // first halo slot (relative to h / w) this rank fills
     int64_t src_begin;          // offset of this peer's list inside the concatenated send list
@@ -25,7 +25,7 @@ struct HaloPeer {
 };
 
 struct HaloPutArgs {
-    const float *h, *w;         // this rank's freshly written buffers
+    const float2 *hw;           // this rank's freshly written {height, water} buffer
     const int32_t *send_idx;    // concatenated local indices, peer after peer
     HaloPeer peer[HALO_MAX_PEERS];
     int npeers;
@@ -44,8 +44,7 @@ halo_put_kernel(const __grid_constant__ HaloPutArgs a)
         for (int q = 1; q < HALO_MAX_PEERS; ++q) if (q < a.npeers && i >= a.peer[q].src_begin) p = q;
         const int64_t j = i - a.peer[p].src_begin;
         const int32_t v = __ldg(a.send_idx + i);
-        a.peer[p].h[a.peer[p].dst_off + j] = a.h[v];
-        a.peer[p].w[a.peer[p].dst_off + j] = a.w[v];
+        a.peer[p].hw[a.peer[p].dst_off + j] = a.hw[v];
     }
     __threadfence_system();                 // this thread's peer stores are visible system-wide ...
     __syncthreads();
@@ -64,21 +63,21 @@ halo_put_kernel(const __grid_constant__ HaloPutArgs a)
 }
 
 // peers_dev: array of npeers structs in host memory (copied by value into the launch)
-NXB_API int nxb_halo_put_f32(const float *h, const float *w, const int32_t *send_idx, int npeers,
-                             void *const *peer_h, void *const *peer_w, void *const *peer_flag,
+NXB_API int nxb_halo_put_f32(const float *hw, const int32_t *send_idx, int npeers,
+                             void *const *peer_hw, void *const *peer_flag,
                              const int64_t *dst_off, const int64_t *src_begin, const int64_t *count,
                              uint32_t flag_value, void *ticket, void *stream)
 {
     NXB_ARG(npeers >= 0 && npeers <= HALO_MAX_PEERS);
     if (npeers == 0) return NXB_OK;
-    NXB_ARG(h && w && send_idx && peer_h && peer_w && peer_flag && dst_off && src_begin && count && ticket);
+    NXB_ARG(hw && send_idx && peer_hw && peer_flag && dst_off && src_begin && count && ticket);
     HaloPutArgs a;
-    a.h = h; a.w = w; a.send_idx = send_idx; a.npeers = npeers; a.flag_value = flag_value;
+    a.hw = (const float2 *)hw; a.send_idx = send_idx; a.npeers = npeers; a.flag_value = flag_value;
     a.ticket = (unsigned int *)ticket;
     int64_t total = 0;
     for (int p = 0; p < npeers; ++p) {
         NXB_ARG(src_begin[p] == total && count[p] >= 0);
-        a.peer[p].h = (float *)peer_h[p]; a.peer[p].w = (float *)peer_w[p]; a.peer[p].flag = (uint32_t *)peer_flag[p];
+        a.peer[p].hw = (float2 *)peer_hw[p]; a.peer[p].flag = (uint32_t *)peer_flag[p];
         a.peer[p].dst_off = dst_off[p]; a.peer[p].src_begin = src_begin[p]; a.peer[p].count = count[p];
         total += count[p];
     }

@@ -38,8 +38,9 @@ def _edge_lengths(nodes, adj):
 
 
 class Erosion3State:
-    """Device-resident state of erode_terrain3: tile plan, edge lengths, (h, water, sediment) x ping-pong.
-    Buffers are padded to a whole number of 256-vertex tiles."""
+    """Device-resident state of erode_terrain3: tile plan, edge lengths, ({height, water}, sediment) x ping-pong.
+    Heights and water are interleaved (float32 [capacity, 2]): a neighbour's two values are always read
+    together, so they travel in one bulk copy / one 8-byte load.  Buffers are padded to whole 256-vertex tiles."""
 
     def __init__(self, nodes, adj, heights32, plan=None, dist=None):
         self.adj = adj
@@ -47,16 +48,16 @@ class Erosion3State:
         self.plan = plan if plan is not None else rt.ErosionPlan(adj)
         self.dist = dist if dist is not None else _edge_lengths(nodes, adj)
         cap, dev = self.plan.capacity, adj.device
-        h = torch.zeros(cap, dtype=rt.F32, device=dev)
-        h[: self.n].copy_(heights32[: self.n])
-        self.cur = (h, torch.zeros(cap, dtype=rt.F32, device=dev), torch.zeros(cap, dtype=rt.F32, device=dev))
-        self.nxt = tuple(torch.zeros(cap, dtype=rt.F32, device=dev) for _ in range(3))
+        hw = torch.zeros((cap, 2), dtype=rt.F32, device=dev)
+        hw[: self.n, 0].copy_(heights32[: self.n])
+        self.cur = (hw, torch.zeros(cap, dtype=rt.F32, device=dev))
+        self.nxt = (torch.zeros((cap, 2), dtype=rt.F32, device=dev), torch.zeros(cap, dtype=rt.F32, device=dev))
         self.iterations = 0
 
     def reset(self, heights32):
-        self.cur[0][: self.n].copy_(heights32[: self.n])
+        self.cur[0].zero_()
+        self.cur[0][: self.n, 0].copy_(heights32[: self.n])
         self.cur[1].zero_()
-        self.cur[2].zero_()
         self.iterations = 0
 
     def step(self, rain=RAIN_AMOUNT):
@@ -75,16 +76,17 @@ class Erosion3State:
 
     @property
     def heights(self):
-        return self.cur[0][: self.n]
+        """float32 [n] view (stride 2) of the interleaved state."""
+        return self.cur[0][: self.n, 0]
 
     @property
     def water(self):
         """Water AFTER the last sweep (the reference's `water` array at that point)."""
-        return self.cur[1][: self.n]
+        return self.cur[0][: self.n, 1]
 
     @property
     def sediment(self):
-        return self.cur[2][: self.n]
+        return self.cur[1][: self.n]
 
 
 def _erode_terrain3_exact(nodes, neighbors, heights, num_iter, return_state):
@@ -216,8 +218,8 @@ def erosion_iteration3(verts, neighbors, r_buff, wat, sed):
     `wat` must already contain this iteration's rain, as in erode_terrain3."""
     adj = _neighbors(neighbors)
     st = Erosion3State(verts, adj, rt.upload_f32(r_buff))
-    st.cur[1][: st.n].copy_(rt.upload_f32(wat))
-    st.cur[2][: st.n].copy_(rt.upload_f32(sed))
+    st.cur[0][: st.n, 1].copy_(rt.upload_f32(wat))
+    st.cur[1][: st.n].copy_(rt.upload_f32(sed))
     st.step(rain=0.0)
     rt.download_f64(st.heights.contiguous(), out=r_buff)
     rt.download_f64(st.water.contiguous(), out=wat)

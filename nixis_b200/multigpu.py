@@ -163,7 +163,8 @@ class ShardedErosion:
             self._buf = torch.zeros(n_state + MAX_FLAGS, dtype=torch.float32, device=dev)
             self._peer_base = None
         c = self.cap
-        self.hw = [(self._buf[0:c], self._buf[c:2 * c]), (self._buf[2 * c:3 * c], self._buf[3 * c:4 * c])]
+        # two buffer sets of interleaved {height, water} pairs, float32 [cap, 2] each
+        self.hw = [self._buf[0:2 * c].view(c, 2), self._buf[2 * c:4 * c].view(c, 2)]
         self.sed = [torch.zeros(c, dtype=torch.float32, device=dev), torch.zeros(c, dtype=torch.float32, device=dev)]
         self.flags = self._buf[4 * c:4 * c + MAX_FLAGS].view(torch.int32)      # one uint32 per source rank
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -236,11 +237,11 @@ class ShardedErosion:
         if self._pending:
             self._await()                   # drain the previous run's last incoming halo
         self.sweeps += 1                    # flag values of the new run never collide with the old run's
-        h, w = self.hw[self.cur]
-        h.zero_(); w.zero_()
-        h[: self.plan.n_own].copy_(heights_own[: self.plan.n_own])
+        hw = self.hw[self.cur]
+        hw.zero_()
+        hw[: self.plan.n_own, 0].copy_(heights_own[: self.plan.n_own])
         self.sed[0].zero_(); self.sed[1].zero_()
-        self.hw[1 - self.cur][0].zero_(); self.hw[1 - self.cur][1].zero_()
+        self.hw[1 - self.cur].zero_()
         if self.world > 1:
             self._barrier()                 # nobody still reads / writes the old run's buffers
         self._publish(self.cur)
@@ -250,16 +251,16 @@ class ShardedErosion:
         if self.world == 1:
             return
         self._pending = True
-        h, w = self.hw[which]
+        hw = self.hw[which]
         if self.transport in ("nvlink", "fused"):
             if not self.send_peers:
                 return
-            ph, pw, pf = self._peer_ptrs(which)
-            _lib.call("nxb_halo_put_f32", rt._ptr(h), rt._ptr(w), rt._ptr(self.send_idx), len(self.send_peers),
-                      ph, pw, pf, self._dst_off, self._src_begin, self._count,
+            ph, pf = self._peer_ptrs(which)
+            _lib.call("nxb_halo_put_f32", rt._ptr(hw), rt._ptr(self.send_idx), len(self.send_peers),
+                      ph, pf, self._dst_off, self._src_begin, self._count,
                       C.c_uint32(self.sweeps + 1), rt._ptr(self.ticket), rt._stream())
         else:
-            exchange_halo_torch(self.plan, [h, w], group=self.group)
+            exchange_halo_torch(self.plan, [hw[:, 0], hw[:, 1]], group=self.group)
 
     def _await(self):
         self._pending = False
@@ -272,11 +273,10 @@ class ShardedErosion:
                           C.c_uint32(self.sweeps + 1), rt._stream())
 
     def _peer_ptrs(self, which):
+        """(peers' hw buffer of set `which`, peers' flag slot for this rank) as seen from this process"""
         c = self.cap
-        off_h = (0 if which == 0 else 2 * c) * 4
-        off_w = (c if which == 0 else 3 * c) * 4
-        return (_ptr_array([self._peer_base[p] + off_h for p in self.send_peers]),
-                _ptr_array([self._peer_base[p] + off_w for p in self.send_peers]),
+        off = (0 if which == 0 else 2 * c) * 4
+        return (_ptr_array([self._peer_base[p] + off for p in self.send_peers]),
                 _ptr_array([self._peer_base[p] + 4 * c * 4 + 4 * self.rank for p in self.send_peers]))
 
     def step(self, rain=RAIN_AMOUNT):
@@ -287,45 +287,33 @@ class ShardedErosion:
         chained with programmatic dependent launch) is issued from C (nxb_erode3_run_comm_f32)."""
         if n <= 0:
             return
-        if self.transport == "fused" and self.world > 1 and self.wait_mode == "kernel":
-            a = self.hw[self.cur] + (self.sed[self.cur],)
-            b = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
-            pa, pb = self._peer_arrays[self.cur], self._peer_arrays[1 - self.cur]
+        if self.transport == "fused" and self.world > 1:
             tp = self.tile_plan
             d3 = tp.dist3_for(self.dist)
-            n_wait = len(self.recv_peers)
-            _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
-                      None if d3 is None else rt._ptr(d3),
-                      rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(a[2]), rt._ptr(b[0]), rt._ptr(b[1]), rt._ptr(b[2]),
-                      tp.n_own, C.c_float(rain), int(n),
-                      rt._ptr(self.send_entries), len(self.send_peers), pa[0], pa[1], pb[0], pb[1], pa[2],
-                      rt._ptr(self.flags), rt._ptr(self.recv_ranks), n_wait,
-                      C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream(),
-                      launches=int(n) * (2 if n_wait else 1))
-            self._pending = True
-            if n % 2:
-                self.cur = 1 - self.cur
-            self.sweeps += n
-            return
-        for _ in range(n):
-            src = self.hw[self.cur] + (self.sed[self.cur],)
-            dst = self.hw[1 - self.cur] + (self.sed[1 - self.cur],)
-            self._await()
-            if self.transport == "fused" and self.world > 1:
+            in_c = self.wait_mode == "kernel"       # the flag waits are issued by the C loop too
+            for n_call in ([n] if in_c else [1] * n):
+                if not in_c:
+                    self._await()
+                a, b = (self.hw[self.cur], self.sed[self.cur]), (self.hw[1 - self.cur], self.sed[1 - self.cur])
                 pa, pb = self._peer_arrays[self.cur], self._peer_arrays[1 - self.cur]
-                tp = self.tile_plan
-                d3 = tp.dist3_for(self.dist)
+                n_wait = len(self.recv_peers) if in_c else 0
                 _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(self.dist),
                           None if d3 is None else rt._ptr(d3),
-                          rt._ptr(src[0]), rt._ptr(src[1]), rt._ptr(src[2]), rt._ptr(dst[0]), rt._ptr(dst[1]), rt._ptr(dst[2]),
-                          tp.n_own, C.c_float(rain), 1,
-                          rt._ptr(self.send_entries), len(self.send_peers), pa[0], pa[1], pb[0], pb[1], pa[2],
-                          rt._ptr(self.flags), rt._ptr(self.recv_ranks), 0,
-                          C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream())
+                          rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(b[0]), rt._ptr(b[1]),
+                          tp.n_own, C.c_float(rain), int(n_call),
+                          rt._ptr(self.send_entries), len(self.send_peers), pa[0], pb[0], pa[1],
+                          rt._ptr(self.flags), rt._ptr(self.recv_ranks), n_wait,
+                          C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream(),
+                          launches=int(n_call) * (2 if n_wait else 1))
                 self._pending = True
-                self.cur = 1 - self.cur
-                self.sweeps += 1
-                continue
+                if n_call % 2:
+                    self.cur = 1 - self.cur
+                self.sweeps += n_call
+            return
+        for _ in range(n):
+            src = (self.hw[self.cur], self.sed[self.cur])
+            dst = (self.hw[1 - self.cur], self.sed[1 - self.cur])
+            self._await()
             rt.erode3_step(self.tile_plan, self.dist, src, dst, rain)
             self.cur = 1 - self.cur
             self.sweeps += 1
@@ -337,11 +325,11 @@ class ShardedErosion:
 
     @property
     def heights(self):
-        return self.hw[self.cur][0][: self.plan.n_own]
+        return self.hw[self.cur][: self.plan.n_own, 0]
 
     @property
     def water(self):
-        return self.hw[self.cur][1][: self.plan.n_own]
+        return self.hw[self.cur][: self.plan.n_own, 1]
 
     @property
     def sediment(self):

@@ -336,19 +336,18 @@ class ErosionPlan:
 
 
 def erode3_step(plan, dist, src, dst, rain):
-    """src/dst: (h, w, s) tuples of float32 CUDA vectors of plan.capacity elements."""
+    """src/dst: (hw, s) pairs: hw float32 [capacity, 2] = {height, water} per vertex, s float32 [capacity]."""
     d3 = plan.dist3_for(dist)
     _lib.call("nxb_erode3_plan_step_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist), None if d3 is None else _ptr(d3),
-              _ptr(src[0]), _ptr(src[1]), _ptr(src[2]), _ptr(dst[0]), _ptr(dst[1]), _ptr(dst[2]),
-              plan.n_own, C.c_float(rain), _stream())
+              _ptr(src[0]), _ptr(src[1]), _ptr(dst[0]), _ptr(dst[1]), plan.n_own, C.c_float(rain), _stream())
 
 
 def erode3_run(plan, dist, a, b, rain, n_sweeps):
-    """erosion.py:180-184 loop in C: n_sweeps sweeps ping-ponging between the (h, w, s) sets a and b
+    """erosion.py:180-184 loop in C: n_sweeps sweeps ping-ponging between the (hw, s) sets a and b
     (sweep 0 reads a).  Returns the set that holds the result."""
     d3 = plan.dist3_for(dist)
     _lib.call("nxb_erode3_run_f32", _ptr(plan.mem), _ptr(plan.adj), _ptr(dist), None if d3 is None else _ptr(d3),
-              _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(b[0]), _ptr(b[1]), _ptr(b[2]),
+              _ptr(a[0]), _ptr(a[1]), _ptr(b[0]), _ptr(b[1]),
               plan.n_own, C.c_float(rain), int(n_sweeps), _stream(), launches=int(n_sweeps))
     return a if n_sweeps % 2 == 0 else b
 
