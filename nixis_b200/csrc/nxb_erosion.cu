@@ -31,6 +31,19 @@
 //     lookup costs nothing.  The explicit-code dist3 variant, the in-kernel flag wait and the
 //     "boundary tiles first" order of round 1 (all measured slower) are gone
 //     from the hot kernel.
+//   * v7 HEIGHT AND WATER INTERLEAVED ({h, w} float2 per vertex): a neighbour's two values are always
+//     read together -- one bulk copy per run instead of two, one 8-byte shared load per neighbour,
+//     one 8-byte peer store per boundary vertex.
+//   * v8 THE VERTEX'S OWN DATA BYPASSES THE BULK-COPY ENGINE.  ncu on v6 (profiles/r02_*): DRAM 59 %,
+//     issue 58 %, and 55 % of all warp stall samples on the consumers' full-barrier wait -- although the
+//     producer never waits for a free stage, pipeline depth 2 runs as fast as depth 3, and an L2
+//     prefetch of the next tiles through cp.async.bulk.prefetch makes the sweep 28 % SLOWER: the time
+//     follows the bytes queued on the per-SM bulk-copy (TMA) engine, ~21 B/clk/SM, whatever their
+//     source.  So only what NEIGHBOURS share is staged (the {h, w} window and runs); the vertex's own
+//     sediment, its six edge lengths (kind 3: dist3[3 v + D_q]; kinds 1 / 2: its row of the full table)
+//     and, on kind-1 tiles, its 16-bit neighbour codes are plain coalesced loads issued before the
+//     barrier wait, which hides their latency: 6.3 KB per tile through the engine instead of 13.7 KB,
+//     and a pipeline stage shrinks from 18 KB to 7.3 KB.
 //   * ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
 //     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
 //   * the sweep LOOP lives here (nxb_erode3_run_*): n sweeps are n launches issued from C with
@@ -41,22 +54,16 @@
 #include <string.h>
 #include <stdlib.h>
 
-#define ERO_STAGES_MAX 4          // pipeline depth is a launch parameter (3: 4 CTAs/SM, 4: 3 CTAs/SM)
+#define ERO_STAGES_MAX 8          // pipeline depth is a launch parameter (a stage is 7.3 KB: only the shared {h, w} values)
 #define ERO_CONSUMER_WARPS (ERO_TILE / 32)
 #define ERO_THREADS (ERO_TILE + 32)
-#define ERO_DIST_FLOATS ((ERO_WIN + ERO_D3_CAP) * 3)
-static_assert(ERO_DIST_FLOATS >= ERO_TILE * 6, "the dist area holds either full rows of the tile or staged dist3 rows");
 
 struct __align__(128) EroStage {
     float2 hw[ERO_STAGE_ELEMS];         // {height, water}; kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
-    float s[ERO_TILE];
-    float dist[ERO_DIST_FLOATS];        // kinds 1/2: [256][6] full rows; kind 3: dist3 rows [window 264 | leading halo slots][3]
-    uint16_t adj[ERO_TILE * 6];         // kind 1 only
     // header, written by producer lane 0 before it arms the full barrier
     int32_t kind, irregular, tile, pad0;
     int32_t send0, send1, pad1, pad2;   // this tile's range of the send-entry list (multi-GPU)
     int32_t affk8[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]
-    int32_t d3k4[8];                    // kind 3: byte offset of slot q's edge length relative to &dist[3 c]
 };
 
 #define ERO_MAX_PEERS 8
@@ -188,7 +195,6 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int d3word = __shfl_sync(0xffffffffu, cur, ERO_DW_D3);
             const int affine = (a.use_affine && !irregular) ? __shfl_sync(0xffffffffu, cur, ERO_DW_AFFINE) : 0;
             const int kind = !affine ? ERO_KIND_CODES : ((a.dist3 != nullptr && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE);
-            const uint32_t d3_rows = kind == ERO_KIND_AFFINE3 ? (uint32_t)(d3word >> 8) : 0u;
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
@@ -196,11 +202,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_OFF + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
-            // header words travel lane -> lane 0: K_q (3 words), dist3 offsets (3 words), send range (2 words)
+            // header words travel lane -> lane 0: K_q (3 words), send range (2 words)
             const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
                       kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
-            const int dk0 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K), dk1 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K + 1),
-                      dk2 = __shfl_sync(0xffffffffu, cur, ERO_DW_D3K + 2);
             const int sd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), sd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
@@ -214,35 +218,15 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     st.affk8[0] = (int)(int16_t)(kw0 & 0xffff) * 8; st.affk8[1] = (kw0 >> 16) * 8;
                     st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
                     st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
-                    uint32_t tx = (uint32_t)(ERO_WIN * 8 + ERO_TILE * 4) + (uint32_t)halo_used * 8u;
-                    if (kind == ERO_KIND_AFFINE3) {
-                        st.d3k4[0] = (int)(int16_t)(dk0 & 0xffff) * 4; st.d3k4[1] = (dk0 >> 16) * 4;
-                        st.d3k4[2] = (int)(int16_t)(dk1 & 0xffff) * 4; st.d3k4[3] = (dk1 >> 16) * 4;
-                        st.d3k4[4] = (int)(int16_t)(dk2 & 0xffff) * 4; st.d3k4[5] = (dk2 >> 16) * 4;
-                        tx += (uint32_t)(ERO_WIN * 12) + d3_rows * 12u;
-                    } else {
-                        tx += (uint32_t)(ERO_TILE * 24);
-                    }
-                    nxb_mbar_expect_tx(&full[s], tx);
+                    nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_WIN * 8) + (uint32_t)halo_used * 8u);
                     nxb_bulk_g2s(st.hw, a.hw_in + v0 - ERO_WIN_PAD, ERO_WIN * 8, &full[s]);
-                    nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
-                    if (kind == ERO_KIND_AFFINE3) nxb_bulk_g2s(st.dist, a.dist3 + (v0 - ERO_WIN_PAD) * 3, ERO_WIN * 12, &full[s]);
-                    else                          nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
                 } else if (q < nseg) {
                     nxb_bulk_g2s(st.hw + ERO_WIN + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
-                    if (seg_off < d3_rows) {
-                        // dist3 rows of the (smaller-numbered) vertices of this run: owners of the backward edges
-                        const uint32_t n3 = min(seg_len, d3_rows - seg_off);
-                        nxb_bulk_g2s(st.dist + (ERO_WIN + seg_off) * 3, a.dist3 + (int64_t)seg_start * 3, n3 * 12u, &full[s]);
-                    }
                 }
             } else if (lane == 0) {
                 const uint32_t halo_bytes = irregular ? 0u : (uint32_t)halo_used * 8u;
-                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * (4 * 3 + 24 + 12)) + halo_bytes);
+                nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_TILE * 8) + halo_bytes);
                 nxb_bulk_g2s(st.hw, a.hw_in + v0, ERO_TILE * 8, &full[s]);
-                nxb_bulk_g2s(st.s, a.s_in + v0, ERO_TILE * 4, &full[s]);
-                nxb_bulk_g2s(st.dist, a.dist + v0 * 6, ERO_TILE * 24, &full[s]);
-                nxb_bulk_g2s(st.adj, a.adj16 + v0 * 6, ERO_TILE * 12, &full[s]);
             } else if (q < nseg && !irregular) {
                 nxb_bulk_g2s(st.hw + ERO_TILE + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
             }
@@ -259,49 +243,61 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const uint32_t full_a0 = nxb_smem_u32(&full[0]), empty_a0 = nxb_smem_u32(&empty[0]);
         uint32_t full_a = full_a0, empty_a = empty_a0;
         const EroStage *stp = stage;
+        const bool d3_on = a.dist3 != nullptr;
         for (int it = 0; it < (int)my_tiles; ++it) {
+            // ---- what this vertex alone needs comes straight from global memory, BEFORE the wait for the
+            // tile's bulk copies: its sediment and, on a kind-3 tile, its six edge lengths (dist3[3 v + D_q],
+            // D_q from the tile descriptor, which the producer pulled through L2 two tiles ago).  These
+            // bytes -- 16 of the 36 B per vertex-sweep -- no longer queue on the bulk-copy engine; their
+            // latency hides behind the barrier wait below.
+            const int64_t tile_g = blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t v = tile_g * ERO_TILE + c;
+            const float so = __ldg(a.s_in + v);                 // buffers are allocated in whole tiles
+            float d[6];
+            uint32_t c0 = 0, c1 = 0, c2 = 0;                    // kind 1: the vertex's six 16-bit neighbour codes
+            {
+                const int32_t *tw = dw + tile_g * ERO_DESC_WORDS;
+                const int4 f = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_NSEG));    // nseg, irregular, halo_used, d3
+                const int aff = (a.use_affine && !f.y) ? __ldg(tw + ERO_DW_AFFINE) : 0;
+                if (aff && d3_on && (f.w & 1)) {                // kind 3: one stored length per edge
+                    const int4 o0 = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_D3OFF));
+                    const int2 o1 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFF45));
+                    const float *dp = a.dist3 + v * 3;
+                    d[0] = __ldg(dp + o0.x); d[1] = __ldg(dp + o0.y); d[2] = __ldg(dp + o0.z);
+                    d[3] = __ldg(dp + o0.w); d[4] = __ldg(dp + o1.x); d[5] = __ldg(dp + o1.y);
+                } else {                                        // kinds 1 / 2: the vertex's full row of six lengths
+                    const float2 *dp = reinterpret_cast<const float2 *>(a.dist + v * 6);
+                    const float2 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+                    d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+                    if (!aff && !f.y) {
+                        const uint32_t *ap = reinterpret_cast<const uint32_t *>(a.adj16 + v * 6);
+                        c0 = __ldg(ap); c1 = __ldg(ap + 1); c2 = __ldg(ap + 2);
+                    }
+                }
+            }
             nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
             const EroStage &st = *stp;
             const int kind = st.kind;
-            const int64_t v = (int64_t)st.tile * ERO_TILE + c;
             int32_t e0 = 0, e1 = 0;
             if (COMM) { e0 = st.send0; e1 = st.send1; }
-            float hn[6], wn[6], d[6];
-            float me, wo, so;
+            float hn[6], wn[6];
+            float me, wo;
             if (kind != ERO_KIND_CODES) {
                 // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
                 const char *hwb = reinterpret_cast<const char *>(st.hw + c);
                 const float2 own = st.hw[c + ERO_WIN_PAD];
-                me = own.x; wo = own.y; so = st.s[c];
+                me = own.x; wo = own.y;
                 const int4 ka = *reinterpret_cast<const int4 *>(st.affk8);
                 const int2 kb = *reinterpret_cast<const int2 *>(st.affk8 + 4);
                 const float2 n0 = lds_f32x2_at(hwb, ka.x), n1 = lds_f32x2_at(hwb, ka.y), n2 = lds_f32x2_at(hwb, ka.z),
                              n3 = lds_f32x2_at(hwb, ka.w), n4 = lds_f32x2_at(hwb, kb.x), n5 = lds_f32x2_at(hwb, kb.y);
                 hn[0] = n0.x; wn[0] = n0.y; hn[1] = n1.x; wn[1] = n1.y; hn[2] = n2.x; wn[2] = n2.y;
                 hn[3] = n3.x; wn[3] = n3.y; hn[4] = n4.x; wn[4] = n4.y; hn[5] = n5.x; wn[5] = n5.y;
-                if (kind == ERO_KIND_AFFINE3) {
-                    // one stored length per edge: own dist3 row (forward slots) or the neighbour's row
-                    // (backward slots), entry and row distance constant over the tile
-                    const char *db = reinterpret_cast<const char *>(st.dist + c * 3);
-                    const int4 da = *reinterpret_cast<const int4 *>(st.d3k4);
-                    const int2 dc = *reinterpret_cast<const int2 *>(st.d3k4 + 4);
-                    d[0] = lds_f32_at(db, da.x); d[1] = lds_f32_at(db, da.y); d[2] = lds_f32_at(db, da.z);
-                    d[3] = lds_f32_at(db, da.w); d[4] = lds_f32_at(db, dc.x); d[5] = lds_f32_at(db, dc.y);
-                } else {
-                    const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
-                    const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
-                    d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
-                }
             } else {
                 const float2 own = st.hw[c];
-                me = own.x; wo = own.y; so = st.s[c];
-                const float2 *dp = reinterpret_cast<const float2 *>(st.dist + c * 6);
-                const float2 d0 = dp[0], d1 = dp[1], d2 = dp[2];
-                d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
+                me = own.x; wo = own.y;
                 if (!st.irregular) {
-                    const uint32_t *ap = reinterpret_cast<const uint32_t *>(st.adj + c * 6);
-                    const uint32_t a0 = ap[0], a1 = ap[1], a2 = ap[2];
-                    const uint32_t code[6] = {a0 & 0xffffu, a0 >> 16, a1 & 0xffffu, a1 >> 16, a2 & 0xffffu, a2 >> 16};
+                    const uint32_t code[6] = {c0 & 0xffffu, c0 >> 16, c1 & 0xffffu, c1 >> 16, c2 & 0xffffu, c2 >> 16};
 #pragma unroll
                     for (int q = 0; q < 6; ++q) { const float2 nq = st.hw[code[q] & ERO_CODE_POS]; hn[q] = nq.x; wn[q] = nq.y; }
                 } else {
@@ -460,22 +456,22 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         d.affine = all_ok;
         for (int q = 0; q < 6; ++q) d.aff_k[q] = (int16_t)(all_ok ? k0[q] : 0);
     }
-    // ---- one length per edge (kind 3): where does slot q's length live in the staged dist3 rows? ----
-    //   forward slot (neighbour index > v): own row, window index c + 4, entry = rank among v's forward slots
-    //   backward slot: the neighbour's row, staging index c + K_q, entry = rank of v among ITS forward slots
-    // The tile qualifies when row distance and entry are the same for all 256 vertices, nobody has
-    // more than 3 forward neighbours, and the backward rows lie in the window or the leading
-    // ERO_D3_CAP halo slots.
+    // ---- one length per edge (kind 3): slot q's length of vertex v is dist3[3 v + D_q] ----
+    //   forward slot (neighbour index > v): own row, entry = rank among v's forward slots        D_q = entry
+    //   backward slot: the neighbour's row, entry = rank of v among ITS forward slots            D_q = 3 (n - v) + entry
+    // The tile qualifies when it is affine, D_q is the same for all 256 vertices and nobody has more
+    // than 3 forward neighbours (rows with more -- mesh skeleton, shard seams -- keep only their first 3
+    // lengths in dist3 and must never be referenced).
     {
         __shared__ int j0[6];
         int jq[6];
         bool ok3 = all_ok != 0;
-        int d3_need = 0, fcnt = 0;
+        int fcnt = 0;
         if (ok3) {                          // (36 scattered reads per vertex, affine tiles only)
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 const int64_t n = nb[q];
-                if (n > v) { jq[q] = ERO_WIN_PAD * 3 + fcnt; ++fcnt; }
+                if (n > v) { jq[q] = fcnt; ++fcnt; }
                 else {
                     int fn = 0, idx = -1;
                     for (int t = 0; t < 6; ++t) {
@@ -483,10 +479,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
                         if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
                     }
                     if (fn > 3 || idx < 0) ok3 = false;
-                    jq[q] = kq[q] * 3 + (idx < 0 ? 0 : idx);
-                    const int pos = c + kq[q];              // staging index of the owner row
-                    if (pos < 0) ok3 = false;
-                    if (pos >= ERO_WIN) d3_need = max(d3_need, pos - ERO_WIN + 1);
+                    jq[q] = (int)(n - v) * 3 + (idx < 0 ? 0 : idx);
                 }
             }
             if (fcnt > 3) ok3 = false;
@@ -497,13 +490,12 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         if (c == 0) for (int q = 0; q < 6; ++q) j0[q] = jq[q];
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 6; ++q) ok3 = ok3 && jq[q] == j0[q] && jq[q] >= 0 && jq[q] < 32768;
-        d3_need = -block_reduce_min(-d3_need, scratch);
-        d3_need = (d3_need + 3) & ~3;
-        if (d3_need > ERO_D3_CAP || d3_need > d.halo_used) ok3 = false;
+        for (int q = 0; q < 6; ++q) ok3 = ok3 && jq[q] == j0[q];
         const int all3 = __syncthreads_and(ok3 ? 1 : 0);
-        d.d3 = all3 ? (1 | (d3_need << 8)) : 0;
-        for (int q = 0; q < 6; ++q) d.d3_k[q] = (int16_t)(all3 ? j0[q] : 0);
+        d.d3 = all3 ? 1 : 0;
+        for (int q = 0; q < 4; ++q) d.d3_off[q] = all3 ? j0[q] : 0;
+        d.d3_off45[0] = all3 ? j0[4] : 0;
+        d.d3_off45[1] = all3 ? j0[5] : 0;
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles

@@ -27,13 +27,14 @@
 //       lives in the row of a: dist3[a][i], i = rank of b among a's larger-numbered ("forward")
 //       neighbours in slot order.  In the mesh interior every vertex has exactly 3 forward
 //       neighbours (next in its row, two in the next row), so dist3 is float[.][3] -- half of the
-//       6-per-vertex table.  On an affine tile the owner row of slot q is at the per-tile constant
-//       staging distance (own row for a forward slot, the neighbour's row c + K_q for a backward
-//       slot) and the entry index is a per-tile constant too, so the lookup is a shared-memory
-//       load at c * 12 + const_q bytes: no decode.  The producer stages the dist3 rows of the
-//       window and of the leading (smaller-numbered) halo runs next to h / w.  36 B / vertex-sweep
-//       from HBM; the rows of the previous mesh row were just streamed by another tile and come
-//       from L2.
+//       6-per-vertex table.  On an affine tile the owner row of slot q is at a per-tile constant
+//       INDEX distance G_q from the vertex (0 for a forward slot, the neighbour's index minus the
+//       vertex's for a backward slot) and the entry is a per-tile constant too, so slot q's length
+//       of vertex v is dist3[3 v + D_q] with D_q = 3 G_q + entry: six coalesced loads per thread,
+//       issued BEFORE the thread waits for the tile's bulk copies -- they, and the vertex's own
+//       sediment, bypass the bulk-copy engine (see nxb_erosion.cu: that engine, not HBM, is what
+//       the staged bytes queue on).  36 B / vertex-sweep from HBM; the rows of the previous mesh
+//       row were just streamed by another tile and come from L2.
 #pragma once
 #include <stdint.h>
 
@@ -47,7 +48,6 @@
 
 #define ERO_WIN_PAD 4
 #define ERO_WIN (ERO_TILE + 2 * ERO_WIN_PAD)     // 264
-#define ERO_D3_CAP 288          // leading halo slots whose dist3 rows can be staged (kind 3)
 #define ERO_KIND_CODES 1
 #define ERO_KIND_AFFINE 2
 #define ERO_KIND_AFFINE3 3
@@ -59,13 +59,12 @@ struct EroTileDesc {            // 128 bytes
     int32_t nseg;
     int32_t irregular;
     int32_t halo_used;
-    int32_t d3;                 // bit 0: tile qualifies for kind 3; bits 8..: leading halo slots whose dist3 rows are staged
+    int32_t d3;                 // bit 0: tile qualifies for kind 3 (d3_off valid)
     int32_t affine;             // 1: implicit adjacency, aff_k valid
     int16_t aff_k[6];           // K_q: staging index of slot q's neighbour minus c (window layout)
-    int16_t d3_k[6];            // kind 3: float index of slot q's length in the staged dist3 rows minus 3 c
-    int32_t pad0;
+    int32_t d3_off[4];          // kind 3: D_q = float index of slot q's length in dist3 minus 3 v, q = 0..3
     int32_t send0, send1;       // multi-GPU shard: this tile's range of the send-entry list (filled by the driver)
-    int32_t pad1[2];
+    int32_t d3_off45[2];        // D_4, D_5
 };
 static_assert(sizeof(EroTileDesc) == 128, "EroTileDesc layout");
 #define ERO_DESC_WORDS 32
@@ -78,5 +77,6 @@ static_assert(sizeof(EroTileDesc) == 128, "EroTileDesc layout");
 #define ERO_DW_D3 (2 * ERO_NSEG + 3)
 #define ERO_DW_AFFINE (2 * ERO_NSEG + 4)
 #define ERO_DW_AFFK (2 * ERO_NSEG + 5)      // 3 words
-#define ERO_DW_D3K (2 * ERO_NSEG + 8)       // 3 words
+#define ERO_DW_D3OFF (2 * ERO_NSEG + 8)     // 4 words (D_0..D_3); D_4, D_5 at ERO_DW_D3OFF45
+#define ERO_DW_D3OFF45 (2 * ERO_NSEG + 14)
 #define ERO_DW_SEND (2 * ERO_NSEG + 12)     // 2 words
