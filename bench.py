@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--octaves", type=int, default=8)
     ap.add_argument("--iters", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--noise-dim", type=int, default=3, choices=[3, 4],
+                    help="4: BASELINE configs[4]'s 4-D fBm (w = 0.5 f per octave; no reference driver exists, SURVEY 0.6)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -245,8 +247,8 @@ def run_reference(args):
 
 def workload_config(args):
     return {"workload": f"icosphere d={args.division} ({10 * args.division ** 2 + 2} verts), {args.octaves}-octave "
-                        f"OpenSimplex fBm + height assembly + {args.iters} erosion_iteration3 sweeps, seed {args.seed}, R=1",
-            "division": args.division, "octaves": args.octaves, "erosion_iters": args.iters,
+                        f"{'4-D ' if args.noise_dim == 4 else ''}OpenSimplex fBm + height assembly + {args.iters} erosion_iteration3 sweeps, seed {args.seed}, R=1",
+            "division": args.division, "octaves": args.octaves, "erosion_iters": args.iters, "noise_dim": args.noise_dim,
             "l2": "inputs larger than L2: every sweep streams 3.2 GB (h/w/s in+out 1.5 GB, edge lengths 1.5 GB, 16-bit adjacency of the non-affine tiles 0.15 GB) vs 126 MB of L2; no flush needed",
             "parallelism": f"vertex-range shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
 
@@ -334,9 +336,10 @@ def run_ours(args):
     k, n_oct, iters = args.division, args.octaves, args.iters
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pipe = TerrainPipeline(k, seed=args.seed, n_octaves=n_oct, radius=1.0)
+    pipe = TerrainPipeline(k, seed=args.seed, n_octaves=n_oct, radius=1.0, noise_dim=args.noise_dim)
     pipe.build_mesh()
-    pipe.mesh.points64()
+    if args.noise_dim == 3:
+        pipe.mesh.points64()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     pipe.erosion_state(torch.zeros(pipe.V, dtype=torch.float32, device=pipe.device))       # tile plan + edge lengths (+ dist3), built once
@@ -414,7 +417,8 @@ def run_ours(args):
     fp32_peak = rt.ffma_peak_tflops()
     ero_launch_ms = ero_ms / iters
     ero_gbs = BYTES_PER_VERT_ITER * V / (ero_launch_ms * 1e-3) / 1e9
-    fbm_tflops = FLOP_PER_VERT_OCT * V * n_oct / (fbm_ms * 1e-3) / 1e12
+    flop_per = FLOP_PER_VERT_OCT if args.noise_dim == 3 else 314.3        # 4-D fBm 314.3 FLOP per vertex-octave
+    fbm_tflops = flop_per * V * n_oct / (fbm_ms * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic_r02(k)
     roofline = {"kernel": "erode3_plan_kernel", "bound": "hbm", "achieved": ero_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ero_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -426,10 +430,10 @@ def run_ours(args):
                         "less (36 B on affine tiles with one stored length per edge, 48 B on other affine tiles: see "
                         "traffic), so frac may exceed 1"}
     fbm_obj = {"value": V * n_oct / (fbm_ms * 1e-3) / 1e6, "unit": "Mvert*octaves/s", "ms": fbm_ms,
-               "roofline": {"kernel": "fbm3_fast_kernel", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
+               "roofline": {"kernel": "fbm3_fast_kernel" if args.noise_dim == 3 else "fbm_kernel<4>", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
                             "unit": "TFLOP/s", "frac": fbm_tflops / fp32_peak,
                             "peak_source": "measured here: nxb_ffma_peak FFMA microbenchmark",
-                            "algorithmic_flop_per_vert_octave": FLOP_PER_VERT_OCT,
+                            "algorithmic_flop_per_vert_octave": flop_per,
                             "note": "lattice cell + candidate selection run in float64 (the reference's own decisions) on the FP64 pipe"}}
     ero_obj = {"value": V * iters / (ero_ms * 1e-3) / 1e6, "unit": "Mvert-iters/s", "ms": ero_ms,
                "nonfinite_heights_after_last_step": nonfinite,
@@ -478,6 +482,8 @@ def run_ours(args):
     del q, maps, h_exp, ocean_exp, h_fin
 
     # ---- end to end through the reference-named API with HOST (pinned) buffers -------------
+    if args.noise_dim == 4:
+        args.no_e2e = args.no_cpu = True             # the reference-named API / the CPU arm have no 4-D fBm driver
     if not args.no_e2e:
         points = pinned(np, torch, (V, 3), torch.float64)
         torch.from_numpy(points).copy_(pipe.mesh.points64())

@@ -62,17 +62,16 @@ struct __align__(128) EroStage {
     float2 hw[ERO_STAGE_ELEMS];         // {height, water}; kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
     // header, written by producer lane 0 before it arms the full barrier
     int32_t kind, irregular, tile, pad0;
-    int32_t send0, send1, pad1, pad2;   // this tile's range of the send-entry list (multi-GPU)
     int32_t affk8[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]
 };
 
 #define ERO_MAX_PEERS 8
+#define ERO_SEND_SCAN 8           // a tile with more send entries (or a vertex sent more than twice) takes the staged path
 
-// One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` of peer slot
-// `peer`'s output buffers.  Entries are grouped by tile; the tile's range [send0, send1) sits in its
-// descriptor, so the producer hands it to the consumers with the rest of the stage header (round 1
-// had every consumer thread fetch it with two dependent global loads per tile: +20 % per sweep on
-// a shard).
+// One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` (< 2^28) of peer
+// slot `peer`'s output buffer.  Entries are grouped by tile; the tile's range [send0, send1) sits in its
+// descriptor (send0 stored as -1 - send0 for a DENSE tile), read by the consumers with their other
+// per-tile words before the barrier wait.
 struct EroSendEntry { int32_t dst; uint16_t c; uint16_t peer; };
 
 // Fused halo exchange (multi-GPU shards; all pointers null / counts zero on a single GPU):
@@ -149,7 +148,7 @@ __device__ __forceinline__ float2 lds_f32x2_at(const char *base, int byte_off)
 // COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop
 // (the sweep is issue-co-limited: each instruction per vertex counts).
 template <bool COMM>
-__global__ void __launch_bounds__(ERO_THREADS)
+__global__ void __launch_bounds__(ERO_THREADS, 5)      // 5 CTAs/SM: <= 40 registers (a stage is 7.3 KB, registers are the limit)
 erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -202,16 +201,12 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_OFF + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
-            // header words travel lane -> lane 0: K_q (3 words), send range (2 words)
+            // header words travel lane -> lane 0: K_q (3 words)
             const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
                       kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
-            const int sd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), sd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
-            if (lane == 0) {
-                st.kind = kind; st.irregular = irregular; st.tile = (int32_t)tile;
-                if (COMM) { st.send0 = sd0; st.send1 = sd1; }
-            }
+            if (lane == 0) { st.kind = kind; st.irregular = irregular; st.tile = (int32_t)tile; }
             if (kind != ERO_KIND_CODES) {
                 // window layout: [v0 - 4, v0 + 260) of h and w, halo runs behind it; no adjacency codes
                 if (lane == 0) {
@@ -275,11 +270,33 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     }
                 }
             }
+            // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
+            // at most twice: the row ends next to the mesh skeleton, 20 % of a shard's tiles with ~3 entries
+            // each) is handled per thread: every thread scans the tile's entries -- uniform loads, issued here,
+            // before the barrier wait -- and keeps the (peer, slot) pairs of ITS vertex; after the math it
+            // stores its own {h, w} straight to the peer.  No block barrier, no staging.  (Round 2, first cut:
+            // every send tile went through two named barriers and a dependent load, 1.1 us per send tile,
+            // +23 us per sweep at 4 GPUs.)  DENSE tiles (seam rows, the skeleton's own tiles) keep the staged path.
+            int32_t e0 = 0, e1 = 0;
+            uint32_t snd0 = 0xffffffffu, snd1 = 0xffffffffu;   // (peer << 28) | slot in the peer's buffer
+            bool dense = false;
+            if (COMM && a.comm.n_send_peers > 0) {
+                const int2 sr = __ldg(reinterpret_cast<const int2 *>(dw + tile_g * ERO_DESC_WORDS + ERO_DW_SEND));
+                dense = sr.x < 0;
+                e0 = dense ? -1 - sr.x : sr.x; e1 = sr.y;
+                if (!dense) {
+                    for (int32_t e = e0; e < e1; ++e) {
+                        const EroSendEntry en = a.comm.send_entries[e];
+                        if (en.c == (uint16_t)c) {
+                            const uint32_t packed = ((uint32_t)en.peer << 28) | (uint32_t)en.dst;
+                            if (snd0 == 0xffffffffu) snd0 = packed; else snd1 = packed;
+                        }
+                    }
+                }
+            }
             nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
             const EroStage &st = *stp;
             const int kind = st.kind;
-            int32_t e0 = 0, e1 = 0;
-            if (COMM) { e0 = st.send0; e1 = st.send1; }
             float hn[6], wn[6];
             float me, wo;
             if (kind != ERO_KIND_CODES) {
@@ -320,13 +337,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
             if (v < a.n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
             if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
-                send_hw[c] = make_float2(hh, ww);
-                asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
-                for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
-                    const EroSendEntry en = a.comm.send_entries[e];
-                    a.comm.peer_hw[en.peer][en.dst] = send_hw[en.c];      // one 8-byte store over NVLink
+                if (!dense) {
+                    if (snd0 != 0xffffffffu) a.comm.peer_hw[snd0 >> 28][snd0 & 0x0fffffffu] = make_float2(hh, ww);   // one 8-byte store over NVLink
+                    if (snd1 != 0xffffffffu) a.comm.peer_hw[snd1 >> 28][snd1 & 0x0fffffffu] = make_float2(hh, ww);
+                } else {
+                    send_hw[c] = make_float2(hh, ww);
+                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
+                    for (int32_t e = e0 + c; e < e1; e += ERO_TILE) {
+                        const EroSendEntry en = a.comm.send_entries[e];
+                        a.comm.peer_hw[en.peer][en.dst] = send_hw[en.c];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(ERO_TILE) : "memory");
                 cta_sent = true;
             }
             if (++s == n_stages) { s = 0; ph_full ^= 1u; full_a = full_a0; empty_a = empty_a0; stp = stage; }

@@ -106,6 +106,7 @@ def _is_gloo(group):
 
 MAX_PEERS = 8       # csrc/nxb_erosion.cu ERO_MAX_PEERS, csrc/nxb_halo.cu HALO_MAX_PEERS
 MAX_FLAGS = 64      # flag slots behind the state buffers (one per source rank)
+SEND_SCAN = 8       # csrc/nxb_erosion.cu ERO_SEND_SCAN
 
 
 class ShardedErosion:
@@ -225,11 +226,22 @@ class ShardedErosion:
             self.send_entries = torch.zeros(1, dtype=torch.int64, device=dev)
         ptr = torch.zeros(n_tiles + 1, dtype=torch.int64, device=dev)
         ptr[1:] = torch.cumsum(counts, 0)
+        # a tile is SPARSE when it has at most SEND_SCAN entries and no vertex occurs more than twice: its
+        # threads then find their own entries by scanning the list (csrc/nxb_erosion.cu); other tiles are DENSE
+        dense = counts > SEND_SCAN
+        if vs:
+            uv, mult = torch.unique(v, return_counts=True)
+            over = torch.zeros(n_tiles, dtype=torch.bool, device=dev)
+            over[(uv[mult > 2] // TILE)] = True
+            dense |= over
+            assert int(dst.max().item()) < (1 << 28), "peer slot index does not fit the packed send word"
         if n_tiles:
             desc = self.tile_plan.descriptors()
-            desc[:, rt.ERO_DW_SEND] = ptr[:-1].to(torch.int32)
+            e0 = ptr[:-1]
+            desc[:, rt.ERO_DW_SEND] = torch.where(dense, -1 - e0, e0).to(torch.int32)
             desc[:, rt.ERO_DW_SEND + 1] = ptr[1:].to(torch.int32)
         self.n_send_tiles = int((counts > 0).sum().item())
+        self.n_dense_send_tiles = int((dense & (counts > 0)).sum().item())
 
     # ------------------------------------------------------------------------------------
     def load(self, heights_own):
@@ -339,8 +351,10 @@ class ShardedErosion:
 class ShardedTerrain:
     """One rank's share of the whole hot path."""
 
-    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, transport="fused", group=None):
+    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, transport="fused", group=None, noise_dim=3, w_scale=0.5):
         rt.require_cuda()
+        assert noise_dim in (3, 4)
+        self.noise_dim, self.w_scale, self.seed, self.n_octaves = int(noise_dim), float(w_scale), seed, int(n_octaves)
         self.k, self.radius, self.group = int(k), float(radius), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -358,7 +372,8 @@ class ShardedTerrain:
         import time
         t0 = time.perf_counter()
         # mesh shard: float64 positions of the own range only (closed form)
-        _, self.xyz64 = rt.mesh_points(self.k, self.begin, self.end, f32=False, f64=True, device=self.device)
+        self.xyz32, self.xyz64 = rt.mesh_points(self.k, self.begin, self.end, f32=(self.noise_dim == 4), f64=(self.noise_dim == 3),
+                                                device=self.device)
         # neighbour rows of the OWN range only, straight from the closed-form triangle generator (no cell
         # array, no whole-mesh table on any rank); the halo plan comes from one exchange of id lists
         rows = rt.icosa_adj_rows(self.k, self.begin, self.end, device=self.device)
@@ -372,6 +387,9 @@ class ShardedTerrain:
         self.setup_ms = {"mesh_rows_plan_edges": (t1 - t0) * 1e3, "tile_plan_peer_memory": (time.perf_counter() - t1) * 1e3}
 
     def fbm(self, out=None, minmax=None):
+        if self.noise_dim == 4:          # BASELINE configs[4]: 4-D noise, w = w_scale * frequency per octave
+            return rt.fbm4(self.tables, self.xyz32, self.freq, self.amp, [self.w_scale * f for f in self.freq],
+                           out=out, minmax=minmax)
         nr = [f / self.radius for f in self.freq]
         return rt.fbm3_pos64(self.tables, self.xyz64, self.radius, nr, self.amp, out=out, minmax=minmax)
 
@@ -412,7 +430,7 @@ def sharded_vs_single_gpu_check(terr, seed, n_octaves, sweeps=25):
     verdict = torch.zeros(2, dtype=torch.int64, device=terr.device)
     sha = ""
     if terr.rank == 0:
-        pipe = TerrainPipeline(terr.k, seed=seed, n_octaves=n_octaves, radius=terr.radius)
+        pipe = TerrainPipeline(terr.k, seed=seed, n_octaves=n_octaves, radius=terr.radius, noise_dim=terr.noise_dim, w_scale=terr.w_scale)
         pipe.build_mesh()
         h1, _, lvl1 = pipe.heights()
         st = pipe.erosion_state(h1)
@@ -446,7 +464,7 @@ def run_multi_gpu_bench(args, rank, world, local, emit=None):
     transport = os.environ.get("NXB_HALO", "fused")
     torch.cuda.synchronize(); dist.barrier()
     t_setup = time.perf_counter()
-    terr = ShardedTerrain(k, seed=args.seed, n_octaves=n_oct, radius=1.0, transport=transport)
+    terr = ShardedTerrain(k, seed=args.seed, n_octaves=n_oct, radius=1.0, transport=transport, noise_dim=args.noise_dim)
     torch.cuda.synchronize(); dist.barrier()
     setup_total_ms = (time.perf_counter() - t_setup) * 1e3
     peak_setup_gib = torch.cuda.max_memory_allocated() / 2 ** 30
@@ -525,7 +543,7 @@ def run_multi_gpu_bench(args, rank, world, local, emit=None):
     # ---- end to end through the reference-named numpy API: every rank passes ITS slices of the same
     # arrays to the same calls (bench.run_e2e, one definition for every N)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.noise_dim == 3:       # the reference-named API has no 4-D fBm driver
         pts = torch.empty((n_own, 3), dtype=torch.float64, pin_memory=True)
         pts.copy_(terr.xyz64)
         nbr = torch.empty((n_own, 6), dtype=torch.int32, pin_memory=True)

@@ -86,8 +86,12 @@ def assemble_heights(h, coll=None, min_alt=MIN_ALT, max_alt=MAX_ALT, ocean_perce
 class TerrainPipeline:
     """One GPU's share of the planet.  world=1 -> the whole planet."""
 
-    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, rank=0, world=1, device=None):
+    def __init__(self, k, seed=0, n_octaves=8, radius=1.0, rank=0, world=1, device=None, noise_dim=3, w_scale=0.5):
+        """noise_dim 4: BASELINE configs[4]'s 4-D fBm (builder-defined driver, the reference has none):
+        octave o samples noise4d(x f_o, y f_o, z f_o, w_scale f_o)."""
         rt.require_cuda()
+        assert noise_dim in (3, 4)
+        self.noise_dim, self.w_scale = int(noise_dim), float(w_scale)
         self.k, self.seed, self.n_octaves, self.radius = int(k), seed, int(n_octaves), float(radius)
         self.rank, self.world = rank, world
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -113,6 +117,9 @@ class TerrainPipeline:
         return self.mesh
 
     def fbm(self, out=None, minmax=None):
+        if self.noise_dim == 4:
+            return rt.fbm4(self.tables, self.mesh.xyz, self.freq, self.amp, [self.w_scale * f for f in self.freq],
+                           out=out, minmax=minmax)
         nr = [f / self.radius for f in self.freq]                     # terrain.py:43 n_freq / world_radius
         return rt.fbm3_pos64(self.tables, self.mesh.points64(), self.radius, nr, self.amp, out=out, minmax=minmax)
 

@@ -1,48 +1,91 @@
+"""torchrun --nproc-per-node N tools/mgpu_time.py : where a sharded sweep's time goes.
+
+Per rank: own vertices, tile kinds, halo / send sizes, the COMPUTE-ONLY time of a sweep on the shard
+(single-GPU instantiation, no exchange) and the time of the exchanging loop; variants via env
+(NXB_ERO_PDL, NXB_SKELETON_COST, NXB_HALO_WAIT)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist
+from nixis_b200 import runtime as rt
 from nixis_b200.multigpu import ShardedTerrain
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 k = int(os.environ.get("MGPU_K", "2500"))
-for transport in os.environ.get("MGPU_TRANSPORTS", "fused,nvlink").split(","):
-    terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport=transport)
+ev = lambda: torch.cuda.Event(enable_timing=True)
+
+
+def gather(vals):
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+for cost in os.environ.get("MGPU_COSTS", "6").split(","):
+    os.environ["NXB_SKELETON_COST"] = cost
+    terr = ShardedTerrain(k, seed=12345, n_octaves=8, transport="fused")
     h, _, _ = terr.heights()
     ero = terr.erosion
-    for n in (100, 400):
-        ero.load(h)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ero.run(n); ero.finish(); e1.record(); torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print(f"[{transport}{' sepwait' if os.environ.get('NXB_FUSED_SEPARATE_WAIT') else ''}] k={k} world={world}: {n} sweeps {ms.item():.2f} ms -> {ms.item()/n*1e3:.1f} us/sweep", flush=True)
-    # per-rank compute-only time (no exchange): load imbalance
-    from nixis_b200 import runtime as rt
-    src = ero.hw[0] + (ero.sed[0],); dst = ero.hw[1] + (ero.sed[1],)
-    for _ in range(5): rt.erode3_step(ero.tile_plan, ero.dist, src, dst, 0.0)
+    tp = ero.tile_plan
+    # compute only: the single-GPU instantiation on this shard's buffers
+    a, b = (ero.hw[0], ero.sed[0]), (ero.hw[1], ero.sed[1])
+    ero.load(h); ero.finish(); torch.cuda.synchronize(); dist.barrier()
+    rt.erode3_run(tp, ero.dist, a, b, 0.0, 20)
     torch.cuda.synchronize(); dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(100): rt.erode3_step(ero.tile_plan, ero.dist, src, dst, 0.0); src, dst = dst, src
-    e1.record(); torch.cuda.synchronize()
-    mine = torch.tensor([e0.elapsed_time(e1) * 10.0], device="cuda")
-    allt = [torch.zeros(1, device="cuda") for _ in range(world)]
-    dist.all_gather(allt, mine)
-    irr = torch.tensor([float(ero.tile_plan.n_irregular)], device="cuda"); alli = [torch.zeros(1, device="cuda") for _ in range(world)]
-    dist.all_gather(alli, irr)
+    e0, e1 = ev(), ev()
+    e0.record(); rt.erode3_run(tp, ero.dist, a, b, 0.0, 200); e1.record(); torch.cuda.synchronize()
+    compute_us = e0.elapsed_time(e1) / 200 * 1e3
+    info = gather([terr.n_own, tp.n_tiles, tp.n_irregular, tp.n_affine, tp.n_affine3, terr.plan.n_halo,
+                   sum(int(v.numel()) for v in terr.plan.send_idx.values()), len(ero.send_peers), len(ero.recv_peers),
+                   getattr(ero, "n_send_tiles", 0), compute_us])
     if rank == 0:
-        print(f"[{transport}] compute-only us/sweep per rank: {[round(t.item(), 1) for t in allt]} irregular tiles per rank: {[int(t.item()) for t in alli]} of {ero.tile_plan.n_tiles}", flush=True)
-    tk = ero.ticket.tolist()
-    rows = sorted([tk[4 + 8 * i: 4 + 8 * i + 8] for i in range(32)], key=lambda r: r[0] & 0xffffffff)
-    rows = [[x & 0xffffffff for x in r] for r in rows if r[0]]
-    base = rows[0][0] if rows else 0
-    us = lambda r, i: f"{(r[i] - r[0]) / 1e3:.0f}" if r[i] else "-"
-    print(f"rank {rank} timeline (start us | +producers dry, +consumers dry, +last CTA past fence, +flag raised): " +
-          " | ".join(f"{(r[0]-base)/1e3:.0f}: +{us(r,4)} +{us(r,5)} +{us(r,6)} +{us(r,2)}" for r in rows[:8]), flush=True)
-    print(f"rank {rank} [{transport}] debug ticket words {tk[:4]} halo tiles {getattr(ero, 'n_halo_tiles', None)} boundary tiles {getattr(ero, 'n_boundary_tiles', None)} mode {getattr(ero, 'fused_mode', None)} of {ero.tile_plan.n_tiles}", flush=True)
+        print(f"== d={k} world={world} skeleton cost {cost}")
+        for r, v in enumerate(info):
+            print(f"  rank {r}: own {int(v[0])} tiles {int(v[1])} irregular {int(v[2])} affine {int(v[3])} kind3 {int(v[4])} halo {int(v[5])} "
+                  f"sent {int(v[6])} peers {int(v[7])}/{int(v[8])} send-tiles {int(v[9])}  compute-only {v[10]:.1f} us/sweep", flush=True)
+    # the exchange-capable instantiation, step by step: (1) no sends, no waits; (2) sends + flags, no waits
+    # (results are garbage, the time is what the peer stores cost); then the real loop
+    import ctypes as C
+    from nixis_b200 import _lib
+    d3 = tp.dist3_for(ero.dist)
+    pa, pb = ero._peer_arrays[0], ero._peer_arrays[1]
+    for label, n_send, n_wait in (("COMM kernel, no sends, no waits", 0, 0), ("COMM kernel, sends + flags, no waits", len(ero.send_peers), 0)):
+        torch.cuda.synchronize(); dist.barrier()
+        def run(n):
+            _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(ero.dist), None if d3 is None else rt._ptr(d3),
+                      rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(b[0]), rt._ptr(b[1]), tp.n_own, C.c_float(0.0), n,
+                      rt._ptr(ero.send_entries), n_send, pa[0], pb[0], pa[1], rt._ptr(ero.flags), rt._ptr(ero.recv_ranks), n_wait,
+                      C.c_uint32(1 << 20), rt._ptr(ero.ticket), rt._stream())
+        run(20)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record(); run(200); e1.record(); torch.cuda.synchronize()
+        t = gather([e0.elapsed_time(e1) / 200 * 1e3])
+        if rank == 0:
+            print(f"  {label}: per rank {[round(x[0], 1) for x in t]} us/sweep", flush=True)
+        dist.barrier()
+    ero.sweeps = (1 << 20) + 400          # keep the flag values monotone for the real loop below
+    for env in ({}, {"NXB_ERO_PDL": "0"}):
+        for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT"):
+            os.environ.pop(key, None)
+        os.environ.update(env)
+        ero.wait_mode = os.environ.get("NXB_HALO_WAIT", "kernel")
+        best = 1e9
+        for rep in range(3):
+            ero.load(h)
+            ero.run(20)
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = ev(), ev()
+            e0.record(); ero.run(300); ero.finish(); e1.record(); torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            best = min(best, ms.item() / 300 * 1e3)
+        if rank == 0:
+            print(f"  exchanging loop {str(env):28s} {best:.1f} us/sweep (max over ranks)", flush=True)
+    for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT"):
+        os.environ.pop(key, None)
+    ero.close()
     del terr, ero
     torch.cuda.empty_cache()
 dist.destroy_process_group()
