@@ -2,6 +2,9 @@
 // util.py:110-254, terrain.py:61-72, nixis.py:332-364.  All HBM-bound streaming kernels:
 // 16-byte vector accesses, grid = whole waves of 148 SMs, one atomic pair per CTA for reductions.
 #include "nxb_common.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 #include <math.h>
 
 #define INF_POS __int_as_float(0x7f800000)
@@ -231,8 +234,12 @@ power_stats_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask
     }
 }
 
+// Scratch (per-CTA summaries + the last-CTA ticket) is keyed by (device, stream): calls on different
+// streams of one device never share a ticket or block_stats array, calls on one stream are ordered by
+// the stream.  The map itself is guarded by a mutex (host threads).
 struct PStatScratch { PStat *blocks; unsigned int *ticket; int cap; };
-static PStatScratch g_pstat[64];
+static std::mutex g_pstat_mutex;
+static std::map<std::pair<int, void *>, PStatScratch> g_pstat;
 
 NXB_API int nxb_power_summary_f32(const float *x, const uint8_t *mask, int64_t n, int sel_mode,
                                   float *summary4, void *stream)
@@ -241,11 +248,14 @@ NXB_API int nxb_power_summary_f32(const float *x, const uint8_t *mask, int64_t n
     NXB_ARG(n == 0 || (x && mask));
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
-    NXB_ARG(dev < 64);
     int grid = nxb_grid_resident(power_stats_kernel, PSTAT_BLOCK, 0, (n + PSTAT_BLOCK * PSTAT_PER_THREAD - 1) / (PSTAT_BLOCK * PSTAT_PER_THREAD));
-    PStatScratch &sc = g_pstat[dev];
+    std::lock_guard<std::mutex> lock(g_pstat_mutex);
+    PStatScratch &sc = g_pstat[std::make_pair(dev, stream)];        // value-initialised (null, 0) on first use
     if (sc.cap < grid) {
-        if (sc.blocks) cudaFree(sc.blocks);
+        if (sc.blocks) {                        // regrow: the stream may still be using the old arrays
+            NXB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(sc.blocks);
+        }
         if (sc.ticket) cudaFree(sc.ticket);
         int cap = nxb_sm_count() * 4;
         if (cap < grid) cap = grid;

@@ -60,18 +60,31 @@
 
 struct __align__(128) EroStage {
     float2 hw[ERO_STAGE_ELEMS];         // {height, water}; kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
-    // header, written by producer lane 0 before it arms the full barrier
-    int32_t kind, irregular, tile, pad0;
-    int32_t affk8[8];                   // kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]
+    // header, written by the producer warp before lane 0 arms the full barrier
+    int32_t kind, irregular;
+    int32_t nmode;                      // what the consumers prefetch for the CTA's NEXT tile (ERO_PRE_*)
+    int32_t pad0;
+    int32_t affk8[8];                   // [0..5] kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]; [6], [7]: this tile's send range
+    uint32_t nd[8];                     // NEXT tile, kind 3: [0..3], [6], [7] = 3 * v0_next + D_q, q = 0..3, 4, 5 (index into dist3 of the tile's vertex 0)
 };
+
+// what a consumer thread loads for itself, one tile ahead (nmode of the stage header)
+#define ERO_PRE_NONE 0                  // no next tile
+#define ERO_PRE_CODES 1                 // full row of six lengths + the 16-bit neighbour codes (kind 1, regular)
+#define ERO_PRE_ROW 2                   // full row of six lengths (kind 2, irregular tiles)
+#define ERO_PRE_D3 3                    // six entries of the one-length-per-edge table (kind 3)
+
+// A vertex's own per-sweep data, loaded straight from global memory ONE TILE AHEAD of its use (the
+// loads are issued right after the barrier wait of the previous tile of this CTA and are consumed an
+// iteration later, so neither the descriptor -> length dependency nor DRAM latency is ever waited for).
+struct EroPre { float so; float d[6]; uint32_t c0, c1, c2; };
 
 #define ERO_MAX_PEERS 8
 #define ERO_SEND_SCAN 8           // a tile with more send entries (or a vertex sent more than twice) takes the staged path
 
 // One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` (< 2^28) of peer
 // slot `peer`'s output buffer.  Entries are grouped by tile; the tile's range [send0, send1) sits in its
-// descriptor (send0 stored as -1 - send0 for a DENSE tile), read by the consumers with their other
-// per-tile words before the barrier wait.
+// descriptor (send0 stored as -1 - send0 for a DENSE tile) and reaches the consumers through the stage header.
 struct EroSendEntry { int32_t dst; uint16_t c; uint16_t peer; };
 
 // Fused halo exchange (multi-GPU shards; all pointers null / counts zero on a single GPU):
@@ -100,22 +113,26 @@ struct EroPlanArgs {
     const float *s_in;
     float2 *hw_out;
     float *s_out;
-    int64_t n_own;
-    float rain;
+    int64_t n_own;                                      // < 2^31: vertices are indexed with 32 bits in the hot loop
+    float rain;                                         // erosion.py:182-183 `water += rain`
+    int rain_on_store;                                  // store water + rain (the NEXT sweep's rained water; not on the last sweep of a run)
     EroComm comm;
 };
 
-// erosion.py:210-267 for one vertex, neighbour values already fetched.
+// erosion.py:210-267 for one vertex, neighbour values already fetched.  PRERAIN: the stored water already
+// holds this sweep's rain (fl(w + rain), added by the previous sweep of the same run when it stored), else
+// it is added here -- the same single rounding either way.
+template <bool PRERAIN>
 __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i, const float (&hn)[6],
                                             const float (&wn)[6], const float (&d)[6], float rain,
                                             float &hh, float &ww, float &ss)
 {
     const float evaporation = (float)(0.1 / 320), solubility = (float)(0.01 / 320), capacity = (float)(0.2 / 320);
-    const float wat_i = wat_own + rain;
+    const float wat_i = PRERAIN ? wat_own : wat_own + rain;
     float sed_amt = sed_i, wat_amt = wat_i;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-        const float wq = wn[q] + rain;
+        const float wq = PRERAIN ? wn[q] : wn[q] + rain;
         // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0.
         //   dh > 0: sed_amt += sol * wq, wat_amt += wq * d;   dh < 0: the same with a minus sign;
         //   dh == 0 or NaN: nothing (erosion.py:232-247).
@@ -136,19 +153,48 @@ __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i
     if (ss > cw) { hh += ss - cw; ss -= ss - cw; }
 }
 
-__device__ __forceinline__ float lds_f32_at(const char *base, int byte_off)
-{
-    return *reinterpret_cast<const float *>(base + byte_off);
-}
 __device__ __forceinline__ float2 lds_f32x2_at(const char *base, int byte_off)
 {
     return *reinterpret_cast<const float2 *>(base + byte_off);
 }
 
-// COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop
-// (the sweep is issue-co-limited: each instruction per vertex counts).
-template <bool COMM>
-__global__ void __launch_bounds__(ERO_THREADS, 5)      // 5 CTAs/SM: <= 40 registers (a stage is 7.3 KB, registers are the limit)
+// base + 4 * idx in ONE instruction (IMAD.WIDE.U32 with a register-pair addend)
+__device__ __forceinline__ const float *ero_f32_at(const float *base, uint32_t idx)
+{
+    const float *r;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
+    return r;
+}
+
+// kind 3: six entries of the one-length-per-edge table; i0..i5 = dist3 index of the TILE's vertex 0 for
+// slot q (3 v0 + D_q), p3 = dist3 + 3 c
+__device__ __forceinline__ void ero_prefetch_d3(const EroPlanArgs &a, const float *p3, uint32_t i0, uint32_t i1, uint32_t i2,
+                                                uint32_t i3, uint32_t i4, uint32_t i5, uint32_t v, EroPre &p)
+{
+    p.so = __ldg(ero_f32_at(a.s_in, v));                        // buffers are allocated in whole tiles
+    p.d[0] = __ldg(ero_f32_at(p3, i0)); p.d[1] = __ldg(ero_f32_at(p3, i1)); p.d[2] = __ldg(ero_f32_at(p3, i2));
+    p.d[3] = __ldg(ero_f32_at(p3, i3)); p.d[4] = __ldg(ero_f32_at(p3, i4)); p.d[5] = __ldg(ero_f32_at(p3, i5));
+}
+
+// kinds 1 / 2 and irregular tiles: the vertex's row of the full table, kind 1 also its 16-bit neighbour codes
+__device__ __forceinline__ void ero_prefetch_row(const EroPlanArgs &a, bool codes, uint32_t v, EroPre &p)
+{
+    p.so = __ldg(ero_f32_at(a.s_in, v));
+    const uint32_t v6 = v * 6u;
+    const float2 *dp = reinterpret_cast<const float2 *>(ero_f32_at(a.dist, v6));
+    const float2 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    p.d[0] = d0.x; p.d[1] = d0.y; p.d[2] = d1.x; p.d[3] = d1.y; p.d[4] = d2.x; p.d[5] = d2.y;
+    if (codes) {
+        const uint32_t *ap = reinterpret_cast<const uint32_t *>(a.adj16 + v6);
+        p.c0 = __ldg(ap); p.c1 = __ldg(ap + 1); p.c2 = __ldg(ap + 2);
+    }
+}
+
+// COMM = false: single-GPU instantiation, every exchange-related test compiled out of the hot loop.
+// PRERAIN: the input water already holds this sweep's rain (every sweep of a run but the first).
+// 4 CTAs per SM (<= 56 registers; the 5-CTA / 40-register build of v8 spills once the prefetch registers exist).
+template <bool COMM, bool PRERAIN>
+__global__ void __launch_bounds__(ERO_THREADS, 4)
 erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -160,8 +206,10 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     bool cta_sent = false;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = (a.n_own + ERO_TILE - 1) / ERO_TILE;
-    const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t n_own = (uint32_t)a.n_own;
+    const uint32_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
+    const uint32_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool d3_on = a.dist3 != nullptr;
 
     // Programmatic dependent launch: let the next kernel of the stream (the flag wait / the next
     // sweep) become resident as this grid's CTAs retire; it blocks in its own griddepcontrol.wait
@@ -172,10 +220,29 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         for (int s = 0; s < ERO_STAGES_MAX; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
         nxb_fence_mbar_init();
     }
-    // the plan is constant: the first descriptor is fetched before the previous sweep has drained
+    // the plan is constant: the first descriptors are fetched before the previous sweep has drained
     const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
-    int32_t word = 0;                           // producer warp: this lane's word of the 32-word descriptor
-    if (warp == 0 && my_tiles > 0) word = __ldg(dw + (int64_t)blockIdx.x * ERO_DESC_WORDS + lane);
+    int32_t word = 0, word_n = 0;               // producer warp: this lane's word of the descriptors of tiles it, it + 1
+    int pmode = ERO_PRE_NONE;                   // consumers: what to load for the CTA's first tile
+    uint32_t idx3[6] = {0, 0, 0, 0, 0, 0};
+    if (my_tiles > 0) {
+        const int32_t *tw = dw + (size_t)blockIdx.x * ERO_DESC_WORDS;
+        if (warp == 0) {
+            word = __ldg(tw + lane);
+            if (my_tiles > 1) word_n = __ldg(tw + (size_t)gridDim.x * ERO_DESC_WORDS + lane);
+        } else {
+            const int4 f = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_NSEG));        // nseg, irregular, halo_used, d3
+            const int aff = (a.use_affine && !f.y) ? __ldg(tw + ERO_DW_AFFINE) : 0;
+            pmode = (aff && d3_on && (f.w & 1)) ? ERO_PRE_D3 : ((aff || f.y) ? ERO_PRE_ROW : ERO_PRE_CODES);
+            if (pmode == ERO_PRE_D3) {
+                const int4 o0 = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_D3OFF));
+                const int2 o1 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFF45));
+                const uint32_t b3 = blockIdx.x * (3u * ERO_TILE);
+                idx3[0] = b3 + (uint32_t)o0.x; idx3[1] = b3 + (uint32_t)o0.y; idx3[2] = b3 + (uint32_t)o0.z;
+                idx3[3] = b3 + (uint32_t)o0.w; idx3[4] = b3 + (uint32_t)o1.x; idx3[5] = b3 + (uint32_t)o1.y;
+            }
+        }
+    }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous sweep's output is complete and visible
 
@@ -183,17 +250,24 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
         int s = 0;
         uint32_t ph_empty = 1;                  // parity the empty barrier of stage s must have passed
-        for (int it = 0; it < (int)my_tiles; ++it) {
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-            const int64_t v0 = tile * ERO_TILE;
-            const int32_t cur = word;           // descriptor words: see ERO_DW_*
-            if (it + 1 < my_tiles) word = __ldg(dw + (tile + gridDim.x) * ERO_DESC_WORDS + lane);
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;
+            const size_t v0 = (size_t)tile * ERO_TILE;
+            const int32_t cur = word, nxt = word_n;     // descriptor words: see ERO_DW_*
+            word = word_n;
+            word_n = (it + 2 < my_tiles) ? __ldg(dw + ((size_t)tile + 2 * (size_t)gridDim.x) * ERO_DESC_WORDS + lane) : 0;
             const int nseg = __shfl_sync(0xffffffffu, cur, ERO_DW_NSEG);
             const int irregular = __shfl_sync(0xffffffffu, cur, ERO_DW_IRREGULAR);
             const int halo_used = __shfl_sync(0xffffffffu, cur, ERO_DW_HALO_USED);
             const int d3word = __shfl_sync(0xffffffffu, cur, ERO_DW_D3);
             const int affine = (a.use_affine && !irregular) ? __shfl_sync(0xffffffffu, cur, ERO_DW_AFFINE) : 0;
-            const int kind = !affine ? ERO_KIND_CODES : ((a.dist3 != nullptr && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE);
+            const int kind = !affine ? ERO_KIND_CODES : ((d3_on && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE);
+            // what the consumers load for themselves for the NEXT tile while they work on this one
+            const int irr_n = __shfl_sync(0xffffffffu, nxt, ERO_DW_IRREGULAR);
+            const int aff_n = (a.use_affine && !irr_n) ? __shfl_sync(0xffffffffu, nxt, ERO_DW_AFFINE) : 0;
+            const int d3_n = __shfl_sync(0xffffffffu, nxt, ERO_DW_D3);
+            const int nmode = it + 1 >= my_tiles ? ERO_PRE_NONE
+                              : ((aff_n && d3_on && (d3_n & 1)) ? ERO_PRE_D3 : ((aff_n || irr_n) ? ERO_PRE_ROW : ERO_PRE_CODES));
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
@@ -201,18 +275,25 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t offs = (uint32_t)__shfl_sync(0xffffffffu, cur, ERO_DW_OFF + (qq >> 1));
             const uint32_t seg_len = (qq & 1) ? (lens >> 16) : (lens & 0xffffu);
             const uint32_t seg_off = (qq & 1) ? (offs >> 16) : (offs & 0xffffu);
-            // header words travel lane -> lane 0: K_q (3 words)
+            // header words travel lane -> lane 0: K_q (3 words), this tile's send range
             const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
                       kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
+            const int snd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), snd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
-            if (lane == 0) { st.kind = kind; st.irregular = irregular; st.tile = (int32_t)tile; }
+            // lanes holding D_q of the next tile turn it into the dist3 index of that tile's vertex 0
+            if (lane >= ERO_DW_D3OFF) st.nd[lane - ERO_DW_D3OFF] = (uint32_t)nxt + (tile + gridDim.x) * (3u * ERO_TILE);
+            if (lane == 0) {
+                st.kind = kind; st.irregular = irregular; st.nmode = nmode;
+                st.affk8[0] = (int)(int16_t)(kw0 & 0xffff) * 8; st.affk8[1] = (kw0 >> 16) * 8;
+                st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
+                st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
+                st.affk8[6] = snd0; st.affk8[7] = snd1;
+            }
+            __syncwarp();                       // the whole header is written before lane 0 arms the barrier
             if (kind != ERO_KIND_CODES) {
-                // window layout: [v0 - 4, v0 + 260) of h and w, halo runs behind it; no adjacency codes
+                // window layout: [v0 - 4, v0 + 260) of {h, w}, halo runs behind it; no adjacency codes
                 if (lane == 0) {
-                    st.affk8[0] = (int)(int16_t)(kw0 & 0xffff) * 8; st.affk8[1] = (kw0 >> 16) * 8;
-                    st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
-                    st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
                     nxb_mbar_expect_tx(&full[s], (uint32_t)(ERO_WIN * 8) + (uint32_t)halo_used * 8u);
                     nxb_bulk_g2s(st.hw, a.hw_in + v0 - ERO_WIN_PAD, ERO_WIN * 8, &full[s]);
                 } else if (q < nseg) {
@@ -234,54 +315,50 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         int s = 0;
         uint32_t ph_full = 0;
         // running shared-window addresses of full[s] / empty[s] and a running stage pointer: the loop
-        // head otherwise re-derives them from s every tile (the sweep is issue-co-limited)
+        // head otherwise re-derives them from s every tile
         const uint32_t full_a0 = nxb_smem_u32(&full[0]), empty_a0 = nxb_smem_u32(&empty[0]);
         uint32_t full_a = full_a0, empty_a = empty_a0;
         const EroStage *stp = stage;
-        const bool d3_on = a.dist3 != nullptr;
-        for (int it = 0; it < (int)my_tiles; ++it) {
-            // ---- what this vertex alone needs comes straight from global memory, BEFORE the wait for the
-            // tile's bulk copies: its sediment and, on a kind-3 tile, its six edge lengths (dist3[3 v + D_q],
-            // D_q from the tile descriptor, which the producer pulled through L2 two tiles ago).  These
-            // bytes -- 16 of the 36 B per vertex-sweep -- no longer queue on the bulk-copy engine; their
-            // latency hides behind the barrier wait below.
-            const int64_t tile_g = blockIdx.x + (int64_t)it * gridDim.x;
-            const int64_t v = tile_g * ERO_TILE + c;
-            const float so = __ldg(a.s_in + v);                 // buffers are allocated in whole tiles
-            float d[6];
-            uint32_t c0 = 0, c1 = 0, c2 = 0;                    // kind 1: the vertex's six 16-bit neighbour codes
+        // ---- what this vertex alone needs comes straight from global memory, one tile AHEAD: its sediment
+        // and its six edge lengths (kind 3: dist3[3 v + D_q]; kinds 1 / 2: its row of the full table; kind 1:
+        // also its 16-bit neighbour codes).  These bytes -- 16 of the 36 B per vertex-sweep on kind-3 tiles --
+        // bypass the bulk-copy engine.  v8 issued them at the top of the tile's own iteration, behind two
+        // dependent descriptor loads: 58 % of all stall samples sat on their first use (profiles/r02_erode3_v8_*).
+        // v9: the producer puts the NEXT tile's words into the stage header, the loads for tile it + 1 are
+        // issued right after the barrier wait of tile it and are consumed an iteration later.
+        // v10: fewer instructions per vertex (187 -> ~115 warp-instructions on a kind-3 tile): 32-bit vertex
+        // and table indices (one IMAD.WIDE per address), the loop unrolled by two so that the two prefetch
+        // register sets swap roles instead of being copied, water stored already rained.
+        const float *p3 = a.dist3 + 3 * c;
+        uint32_t v = blockIdx.x * (uint32_t)ERO_TILE + (uint32_t)c;
+        const uint32_t v_step = gridDim.x * (uint32_t)ERO_TILE;
+
+        auto body = [&](const EroPre &cur, EroPre &nxt) {
+            nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
+            const EroStage &st = *stp;
+            const int kind = st.kind;
             {
-                const int32_t *tw = dw + tile_g * ERO_DESC_WORDS;
-                const int4 f = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_NSEG));    // nseg, irregular, halo_used, d3
-                const int aff = (a.use_affine && !f.y) ? __ldg(tw + ERO_DW_AFFINE) : 0;
-                if (aff && d3_on && (f.w & 1)) {                // kind 3: one stored length per edge
-                    const int4 o0 = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_D3OFF));
-                    const int2 o1 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFF45));
-                    const float *dp = a.dist3 + v * 3;
-                    d[0] = __ldg(dp + o0.x); d[1] = __ldg(dp + o0.y); d[2] = __ldg(dp + o0.z);
-                    d[3] = __ldg(dp + o0.w); d[4] = __ldg(dp + o1.x); d[5] = __ldg(dp + o1.y);
-                } else {                                        // kinds 1 / 2: the vertex's full row of six lengths
-                    const float2 *dp = reinterpret_cast<const float2 *>(a.dist + v * 6);
-                    const float2 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-                    d[0] = d0.x; d[1] = d0.y; d[2] = d1.x; d[3] = d1.y; d[4] = d2.x; d[5] = d2.y;
-                    if (!aff && !f.y) {
-                        const uint32_t *ap = reinterpret_cast<const uint32_t *>(a.adj16 + v * 6);
-                        c0 = __ldg(ap); c1 = __ldg(ap + 1); c2 = __ldg(ap + 2);
-                    }
+                const int nmode = st.nmode;
+                if (nmode == ERO_PRE_D3) {
+                    const uint4 o0 = *reinterpret_cast<const uint4 *>(st.nd);
+                    const uint2 o1 = *reinterpret_cast<const uint2 *>(st.nd + 6);
+                    ero_prefetch_d3(a, p3, o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, v + v_step, nxt);
+                } else if (nmode != ERO_PRE_NONE) {
+                    ero_prefetch_row(a, nmode == ERO_PRE_CODES, v + v_step, nxt);
                 }
             }
             // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
             // at most twice: the row ends next to the mesh skeleton, 20 % of a shard's tiles with ~3 entries
-            // each) is handled per thread: every thread scans the tile's entries -- uniform loads, issued here,
-            // before the barrier wait -- and keeps the (peer, slot) pairs of ITS vertex; after the math it
-            // stores its own {h, w} straight to the peer.  No block barrier, no staging.  (Round 2, first cut:
-            // every send tile went through two named barriers and a dependent load, 1.1 us per send tile,
-            // +23 us per sweep at 4 GPUs.)  DENSE tiles (seam rows, the skeleton's own tiles) keep the staged path.
+            // each) is handled per thread: every thread scans the tile's entries -- uniform loads -- and keeps
+            // the (peer, slot) pairs of ITS vertex; after the math it stores its own {h, w} straight to the
+            // peer.  No block barrier, no staging.  (Round 2, first cut: every send tile went through two named
+            // barriers and a dependent load, 1.1 us per send tile, +23 us per sweep at 4 GPUs.)  DENSE tiles
+            // (seam rows, the skeleton's own tiles) keep the staged path.
             int32_t e0 = 0, e1 = 0;
             uint32_t snd0 = 0xffffffffu, snd1 = 0xffffffffu;   // (peer << 28) | slot in the peer's buffer
             bool dense = false;
             if (COMM && a.comm.n_send_peers > 0) {
-                const int2 sr = __ldg(reinterpret_cast<const int2 *>(dw + tile_g * ERO_DESC_WORDS + ERO_DW_SEND));
+                const int2 sr = *reinterpret_cast<const int2 *>(st.affk8 + 6);
                 dense = sr.x < 0;
                 e0 = dense ? -1 - sr.x : sr.x; e1 = sr.y;
                 if (!dense) {
@@ -294,9 +371,6 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     }
                 }
             }
-            nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
-            const EroStage &st = *stp;
-            const int kind = st.kind;
             float hn[6], wn[6];
             float me, wo;
             if (kind != ERO_KIND_CODES) {
@@ -314,18 +388,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 const float2 own = st.hw[c];
                 me = own.x; wo = own.y;
                 if (!st.irregular) {
-                    const uint32_t code[6] = {c0 & 0xffffu, c0 >> 16, c1 & 0xffffu, c1 >> 16, c2 & 0xffffu, c2 >> 16};
+                    const uint32_t code[6] = {cur.c0 & 0xffffu, cur.c0 >> 16, cur.c1 & 0xffffu, cur.c1 >> 16, cur.c2 & 0xffffu, cur.c2 >> 16};
 #pragma unroll
                     for (int q = 0; q < 6; ++q) { const float2 nq = st.hw[code[q] & ERO_CODE_POS]; hn[q] = nq.x; wn[q] = nq.y; }
                 } else {
                     // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
-                    const int64_t vv = v < a.n_own ? v : a.n_own - 1;
-                    const int2 *rp = reinterpret_cast<const int2 *>(a.adj + vv * 6);
+                    const uint32_t vv = v < n_own ? v : n_own - 1;
+                    const int2 *rp = reinterpret_cast<const int2 *>(a.adj + (size_t)vv * 6);
                     const int2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
                     const int32_t row[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
-                        const int64_t n = row[q] < 0 ? vv : (int64_t)row[q];
+                        const uint32_t n = row[q] < 0 ? vv : (uint32_t)row[q];
                         const float2 nq = __ldg(a.hw_in + n);
                         hn[q] = nq.x; wn[q] = nq.y;
                     }
@@ -334,8 +408,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
             float hh, ww, ss;
-            erode3_math(me, wo, so, hn, wn, d, a.rain, hh, ww, ss);
-            if (v < a.n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
+            erode3_math<PRERAIN>(me, wo, cur.so, hn, wn, cur.d, a.rain, hh, ww, ss);
+            if (a.rain_on_store) ww += a.rain;              // the next sweep's `water += rain`, erosion.py:182-183
+            if (v < n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
             if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
                 if (!dense) {
                     if (snd0 != 0xffffffffu) a.comm.peer_hw[snd0 >> 28][snd0 & 0x0fffffffu] = make_float2(hh, ww);   // one 8-byte store over NVLink
@@ -353,6 +428,16 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             }
             if (++s == n_stages) { s = 0; ph_full ^= 1u; full_a = full_a0; empty_a = empty_a0; stp = stage; }
             else { full_a += 8; empty_a += 8; ++stp; }
+            v += v_step;
+        };
+
+        EroPre pa, pb;
+        pa.c0 = pa.c1 = pa.c2 = pb.c0 = pb.c1 = pb.c2 = 0u;
+        if (pmode == ERO_PRE_D3) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pa);
+        else if (pmode != ERO_PRE_NONE) ero_prefetch_row(a, pmode == ERO_PRE_CODES, v, pa);
+        for (uint32_t it = 0; it < my_tiles; it += 2) {
+            body(pa, pb);
+            if (it + 1 < my_tiles) body(pb, pa);
         }
     }
     if (COMM && a.comm.n_send_peers > 0) {
@@ -628,18 +713,21 @@ static int ero_launch_cfg(int64_t n_own, EroLaunchCfg &cfg)
     NXB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !g_ero_attr_set[dev]) {
         const int max_smem = (int)(sizeof(EroStage) * ERO_STAGES_MAX);
-        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NXB_CUDA(cudaFuncSetAttribute(erode3_plan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         g_ero_attr_set[dev] = true;
     }
     const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
-    cfg.grid[0] = nxb_grid_resident(erode3_plan_kernel<false>, ERO_THREADS, cfg.smem, n_tiles);
-    cfg.grid[1] = nxb_grid_resident(erode3_plan_kernel<true>, ERO_THREADS, cfg.smem, n_tiles);
+    cfg.grid[0] = nxb_grid_resident(erode3_plan_kernel<false, true>, ERO_THREADS, cfg.smem, n_tiles);
+    cfg.grid[1] = nxb_grid_resident(erode3_plan_kernel<true, true>, ERO_THREADS, cfg.smem, n_tiles);
     return NXB_OK;
 }
 
+// prerain: the input water already holds this sweep's rain (stored so by the previous sweep of the run)
 template <bool COMM>
-static int ero_launch(const EroLaunchCfg &cfg, const EroPlanArgs &a, cudaStream_t st)
+static int ero_launch(const EroLaunchCfg &cfg, const EroPlanArgs &a, bool prerain, cudaStream_t st)
 {
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
@@ -652,7 +740,8 @@ static int ero_launch(const EroLaunchCfg &cfg, const EroPlanArgs &a, cudaStream_
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = cfg.pdl ? 1 : 0;
-    NXB_CUDA(cudaLaunchKernelEx(&lc, erode3_plan_kernel<COMM>, a));
+    if (prerain) NXB_CUDA(cudaLaunchKernelEx(&lc, erode3_plan_kernel<COMM, true>, a));
+    else NXB_CUDA(cudaLaunchKernelEx(&lc, erode3_plan_kernel<COMM, false>, a));
     return NXB_OK;
 }
 
@@ -661,6 +750,7 @@ static int ero_base_args(EroPlanArgs &a, const EroLaunchCfg &cfg, const void *pl
 {
     NXB_ARG(plan_mem && adj && dist);
     NXB_ARG((((uintptr_t)plan_mem | (uintptr_t)dist | (uintptr_t)dist3) & 15) == 0);
+    NXB_ARG(n_own < ((int64_t)1 << 30));                    // 32-bit vertex / table indices in the sweep (3 v + D_q, 6 v)
     const int64_t n_tiles = (n_own + ERO_TILE - 1) / ERO_TILE;
     memset(&a, 0, sizeof a);
     a.desc = (const EroTileDesc *)plan_mem;
@@ -683,6 +773,9 @@ static int ero_set_buffers(EroPlanArgs &a, const float *hw_in, const float *s_in
 
 // n_sweeps sweeps, ping-pong between buffer sets A and B (sweep 0 reads A): the result is in A when
 // n_sweeps is even, in B when it is odd.  hw_*: {height, water} interleaved, float[capacity][2].
+// Between the sweeps of one call the stored water is fl(water + rain) -- the next sweep's rained water,
+// the same single rounding erosion.py:182-183 applies -- so only the first sweep adds the rain when it
+// loads; the last sweep stores the plain water (what the caller sees is the reference's state).
 NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const float *dist, const float *dist3,
                                float *hw_a, float *s_a, float *hw_b, float *s_b,
                                int64_t n_own, float rain, int64_t n_sweeps, void *stream)
@@ -697,7 +790,8 @@ NXB_API int nxb_erode3_run_f32(const void *plan_mem, const int32_t *adj, const f
     for (int64_t i = 0; i < n_sweeps; ++i) {
         rc = (i & 1) ? ero_set_buffers(a, hw_b, s_b, hw_a, s_a) : ero_set_buffers(a, hw_a, s_a, hw_b, s_b);
         if (rc) return rc;
-        if ((rc = ero_launch<false>(cfg, a, (cudaStream_t)stream))) return rc;
+        a.rain_on_store = i + 1 < n_sweeps;
+        if ((rc = ero_launch<false>(cfg, a, i > 0, (cudaStream_t)stream))) return rc;
     }
     return NXB_OK;
 }
@@ -750,7 +844,8 @@ NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, co
             a.comm.ticket = (unsigned int *)ticket;
             a.comm.flag_value = sweep_base + 2u + (uint32_t)i;
         }
-        if ((rc = ero_launch<true>(cfg, a, (cudaStream_t)stream))) return rc;
+        a.rain_on_store = i + 1 < n_sweeps;         // what goes to the peers is what is stored: consistent on every rank
+        if ((rc = ero_launch<true>(cfg, a, i > 0, (cudaStream_t)stream))) return rc;
     }
     return NXB_OK;
 }

@@ -44,6 +44,22 @@ static inline uint32_t nxf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); ret
 #define nxf_fma(a, b, c) fmaf(a, b, c)
 #endif
 
+// ---- packed pairs of floats: sm_100a has two-wide FP32 instructions (FFMA2 / FADD2 / FMUL2, one issue slot
+// for two results).  The kernel is issue-bound, so the ten contributions of an evaluation are computed as
+// five PAIRS.  Host build: plain scalar code with the same roundings.
+#ifdef __CUDACC__
+typedef float2 nxf_f2;
+#define nxf_fma2(a, b, c) __ffma2_rn(a, b, c)
+#define nxf_add2(a, b) __fadd2_rn(a, b)
+#define nxf_mul2(a, b) __fmul2_rn(a, b)
+#else
+struct nxf_f2 { float x, y; };
+static inline nxf_f2 nxf_fma2(nxf_f2 a, nxf_f2 b, nxf_f2 c) { nxf_f2 r = {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; return r; }
+static inline nxf_f2 nxf_add2(nxf_f2 a, nxf_f2 b) { nxf_f2 r = {a.x + b.x, a.y + b.y}; return r; }
+static inline nxf_f2 nxf_mul2(nxf_f2 a, nxf_f2 b) { nxf_f2 r = {a.x * b.x, a.y * b.y}; return r; }
+#endif
+NXF_DEV nxf_f2 nxf_mk2(float x, float y) { nxf_f2 r; r.x = x; r.y = y; return r; }
+
 #define NXF_ROW 128u                    // bytes per table row (32 lanes x 4 B)
 #define NXF_MASK 0x7F80u                // (e & 255) * 128
 #define NXF_TAB_BYTES (256u * NXF_ROW)  // one replicated 256-entry table: 32 KB
@@ -57,7 +73,7 @@ static inline uint32_t nxf_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); ret
 
 // record of one non-cube extra lattice point: displacement constants (offset + m/3), the live
 // constant T (2, or -16 for "no extra"), hash offsets pre-multiplied by the row pitch
-struct NxfExtra { float cx, cy, cz, T; int32_t ox, oy, oz, pad; };
+struct NxfExtra { float ncx, ncy, ncz, nT; int32_t ox, oy, oz, pad; };   // -(offset + m/3), -T
 
 // offsets of the 18 non-cube extras, in the order the selection logic indexes them
 //  0..5   tet(0,0,0), (0,0,0) among the two closest: axis k -> 2k, 2k+1     (opensimplex.py:321-350)
@@ -82,6 +98,7 @@ struct NxfCtx {
     uint32_t xb7, yb7, zb7; // (lattice base & 255) * 128, unmasked
     float dx0, dy0, dz0;
     float v;
+    nxf_f2 v2;              // packed accumulator of the five contribution pairs
 };
 
 #ifdef __CUDACC__
@@ -119,33 +136,44 @@ NXF_DEV uint32_t nxf_hash(const NxfCtx &c, uint32_t h_plus_add)
     return nxf_ldu(c, NXF_OFF_P, (h_plus_add & NXF_MASK) | c.lane4);
 }
 
-// contribution of the lattice point whose last-level table index is idx (bytes) and whose
-// displacement is (dx,dy,dz); T is 2 for a live point, -16 for a dead one
-NXF_DEV void nxf_contrib(NxfCtx &c, uint32_t idx, float dx, float dy, float dz, float T)
+// contributions of TWO lattice points at once: last-level table indices idxA / idxB (bytes), displacement
+// pairs d = {d_A, d_B} per axis, nT = {-T_A, -T_B} (T = 2 for a live point, -16 for a dead one).
+//   acc = |d|^2 - T = -attn (same roundings as T - |d|^2, sign flipped); m = min(acc, 0) = -max(attn, 0);
+//   contribution = m^4 * (g . d)
+NXF_DEV void nxf_contrib2(NxfCtx &c, uint32_t idxA, uint32_t idxB, nxf_f2 dx, nxf_f2 dy, nxf_f2 dz, nxf_f2 nT)
 {
-    float at = nxf_fma(-dz, dz, nxf_fma(-dy, dy, nxf_fma(-dx, dx, T)));
-    at = fmaxf(at, 0.0f);
-    const float gx = nxf_ldf(c, NXF_OFF_GX, idx), gy = nxf_ldf(c, NXF_OFF_GY, idx), gz = nxf_ldf(c, NXF_OFF_GZ, idx);
-    const float dot = nxf_fma(gz, dz, nxf_fma(gy, dy, gx * dx));
-    at *= at;
-    c.v = nxf_fma(at * at, dot, c.v);
+    nxf_f2 acc = nxf_fma2(dz, dz, nxf_fma2(dy, dy, nxf_fma2(dx, dx, nT)));
+    const nxf_f2 gx = nxf_mk2(nxf_ldf(c, NXF_OFF_GX, idxA), nxf_ldf(c, NXF_OFF_GX, idxB));
+    const nxf_f2 gy = nxf_mk2(nxf_ldf(c, NXF_OFF_GY, idxA), nxf_ldf(c, NXF_OFF_GY, idxB));
+    const nxf_f2 gz = nxf_mk2(nxf_ldf(c, NXF_OFF_GZ, idxA), nxf_ldf(c, NXF_OFF_GZ, idxB));
+    const nxf_f2 dot = nxf_fma2(gz, dz, nxf_fma2(gy, dy, nxf_mul2(gx, dx)));
+    nxf_f2 m = nxf_mk2(fminf(acc.x, 0.0f), fminf(acc.y, 0.0f));
+    m = nxf_mul2(m, m);
+    c.v2 = nxf_fma2(nxf_mul2(m, m), dot, c.v2);
 }
 
-template <int I, int J, int K>
-NXF_DEV void nxf_corner(NxfCtx &c, uint32_t hxy, float T)
+template <int IA, int JA, int KA, int IB, int JB, int KB>
+NXF_DEV void nxf_corner2(NxfCtx &c, nxf_f2 dx0, nxf_f2 dy0, nxf_f2 dz0, uint32_t hA, uint32_t hB, float TA, float TB)
 {
-    constexpr float m3 = (float)(I + J + K) * (1.0f / 3.0f);
-    const uint32_t idx = ((hxy + c.zb7 + (uint32_t)K * NXF_ROW) & NXF_MASK) | c.lane4;
-    nxf_contrib(c, idx, c.dx0 - ((float)I + m3), c.dy0 - ((float)J + m3), c.dz0 - ((float)K + m3), T);
+    constexpr float mA = (float)(IA + JA + KA) * (1.0f / 3.0f), mB = (float)(IB + JB + KB) * (1.0f / 3.0f);
+    const uint32_t idxA = ((hA + c.zb7 + (uint32_t)KA * NXF_ROW) & NXF_MASK) | c.lane4;
+    const uint32_t idxB = ((hB + c.zb7 + (uint32_t)KB * NXF_ROW) & NXF_MASK) | c.lane4;
+    nxf_contrib2(c, idxA, idxB,
+                 nxf_add2(dx0, nxf_mk2(-((float)IA + mA), -((float)IB + mB))),
+                 nxf_add2(dy0, nxf_mk2(-((float)JA + mA), -((float)JB + mB))),
+                 nxf_add2(dz0, nxf_mk2(-((float)KA + mA), -((float)KB + mB))), nxf_mk2(-TA, -TB));
 }
 
-NXF_DEV void nxf_extra(NxfCtx &c, int e)
+NXF_DEV void nxf_extra2(NxfCtx &c, nxf_f2 dx0, nxf_f2 dy0, nxf_f2 dz0, int e0, int e1)
 {
-    const NxfExtra &r = *reinterpret_cast<const NxfExtra *>(c.sm + NXF_OFF_EXT + (uint32_t)e * 32u);
-    uint32_t h = nxf_hash(c, c.xb7 + (uint32_t)r.ox);
-    h = nxf_hash(c, h + c.yb7 + (uint32_t)r.oy);
-    const uint32_t idx = ((h + c.zb7 + (uint32_t)r.oz) & NXF_MASK) | c.lane4;
-    nxf_contrib(c, idx, c.dx0 - r.cx, c.dy0 - r.cy, c.dz0 - r.cz, r.T);
+    const NxfExtra &r0 = *reinterpret_cast<const NxfExtra *>(c.sm + NXF_OFF_EXT + (uint32_t)e0 * 32u);
+    const NxfExtra &r1 = *reinterpret_cast<const NxfExtra *>(c.sm + NXF_OFF_EXT + (uint32_t)e1 * 32u);
+    uint32_t h0 = nxf_hash(c, c.xb7 + (uint32_t)r0.ox), h1 = nxf_hash(c, c.xb7 + (uint32_t)r1.ox);
+    h0 = nxf_hash(c, h0 + c.yb7 + (uint32_t)r0.oy); h1 = nxf_hash(c, h1 + c.yb7 + (uint32_t)r1.oy);
+    const uint32_t idx0 = ((h0 + c.zb7 + (uint32_t)r0.oz) & NXF_MASK) | c.lane4;
+    const uint32_t idx1 = ((h1 + c.zb7 + (uint32_t)r1.oz) & NXF_MASK) | c.lane4;
+    nxf_contrib2(c, idx0, idx1, nxf_add2(dx0, nxf_mk2(r0.ncx, r1.ncx)), nxf_add2(dy0, nxf_mk2(r0.ncy, r1.ncy)),
+                 nxf_add2(dz0, nxf_mk2(r0.ncz, r1.ncz)), nxf_mk2(r0.nT, r1.nT));
 }
 
 // opensimplex.py:306-312 / 421-427 / 584-599: keep the two best of three candidates.
@@ -317,24 +345,22 @@ NXF_DEV void nxf_select(float fx, float fy, float fz, float fsum,
     nxf_select_r<float>(fx, fy, fz, fsum, T000, T100, T010, T001, T110, T101, T011, T111, e0, e1);
 }
 
-// the 8 cube corners: shared hash tree (2 + 4 lookups), one leaf each; then the two non-cube extras
+// the 8 cube corners: shared hash tree (2 + 4 lookups), one leaf each, evaluated as four PAIRS; the two
+// non-cube extras are the fifth pair
 NXF_DEV float nxf_contributions(NxfCtx &c, float T000, float T100, float T010, float T001,
                                 float T110, float T101, float T011, float T111, int e0, int e1)
 {
     const uint32_t hx0 = nxf_hash(c, c.xb7), hx1 = nxf_hash(c, c.xb7 + NXF_ROW);
     const uint32_t h00 = nxf_hash(c, hx0 + c.yb7), h01 = nxf_hash(c, hx0 + c.yb7 + NXF_ROW);
     const uint32_t h10 = nxf_hash(c, hx1 + c.yb7), h11 = nxf_hash(c, hx1 + c.yb7 + NXF_ROW);
-    nxf_corner<0, 0, 0>(c, h00, T000);
-    nxf_corner<1, 0, 0>(c, h10, T100);
-    nxf_corner<0, 1, 0>(c, h01, T010);
-    nxf_corner<0, 0, 1>(c, h00, T001);
-    nxf_corner<1, 1, 0>(c, h11, T110);
-    nxf_corner<1, 0, 1>(c, h10, T101);
-    nxf_corner<0, 1, 1>(c, h01, T011);
-    nxf_corner<1, 1, 1>(c, h11, T111);
-    nxf_extra(c, e0);
-    nxf_extra(c, e1);
-    return c.v;
+    const nxf_f2 dx0 = nxf_mk2(c.dx0, c.dx0), dy0 = nxf_mk2(c.dy0, c.dy0), dz0 = nxf_mk2(c.dz0, c.dz0);
+    c.v2 = nxf_mk2(0.0f, 0.0f);
+    nxf_corner2<0, 0, 0, 1, 1, 1>(c, dx0, dy0, dz0, h00, h11, T000, T111);
+    nxf_corner2<1, 0, 0, 0, 1, 1>(c, dx0, dy0, dz0, h10, h01, T100, T011);
+    nxf_corner2<0, 1, 0, 1, 0, 1>(c, dx0, dy0, dz0, h01, h10, T010, T101);
+    nxf_corner2<0, 0, 1, 1, 1, 0>(c, dx0, dy0, dz0, h00, h11, T001, T110);
+    nxf_extra2(c, dx0, dy0, dz0, e0, e1);
+    return c.v2.x + c.v2.y;
 }
 
 // ---- float64 prologue + selection (device: __dadd_rn / __dmul_rn are never contracted into FMAs;
@@ -407,8 +433,8 @@ NXF_DEV void nxf_build_tables(const uint8_t *perm8, const uint8_t *grad8, char *
     for (int e = tid; e < 19; e += nthreads) {
         const int8_t *o = NXF_EXTRA_OFFSETS[e];
         const float cc = (float)(o[0] + o[1] + o[2]) * (1.0f / 3.0f);
-        rec[e].cx = (float)o[0] + cc; rec[e].cy = (float)o[1] + cc; rec[e].cz = (float)o[2] + cc;
-        rec[e].T = e == 18 ? -16.0f : 2.0f;
+        rec[e].ncx = -((float)o[0] + cc); rec[e].ncy = -((float)o[1] + cc); rec[e].ncz = -((float)o[2] + cc);
+        rec[e].nT = e == 18 ? 16.0f : -2.0f;
         rec[e].ox = o[0] * (int)NXF_ROW; rec[e].oy = o[1] * (int)NXF_ROW; rec[e].oz = o[2] * (int)NXF_ROW;
         rec[e].pad = 0;
     }

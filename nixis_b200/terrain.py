@@ -131,7 +131,9 @@ def sample_octaves4(verts, elevations, perm, n_octaves=1, n_init_roughness=1.5, 
 
 
 def make_bool_elevation_mask(height, mask_elevation):
-    """mask[h] = height[h] <= mask_elevation (terrain.py:61-72)."""
+    """mask[h] = height[h] <= mask_elevation (terrain.py:61-72).  Device arithmetic is FP32: float64 numpy
+    input (and the level) is rounded to float32 before the comparison, so a vertex within one float32
+    ulp of the level may land on the other side than in the reference."""
     if isinstance(height, torch.Tensor):
         return rt.mask_le(height, float(mask_elevation))
     h = rt.upload_f32(height)

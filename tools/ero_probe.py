@@ -18,9 +18,9 @@ st = pipe.erosion_state(h)
 p = st.plan
 print(f"d={k}: V={pipe.V} tiles {p.n_tiles} irregular {p.n_irregular} affine {p.n_affine} one-length-per-edge {p.n_affine3}", flush=True)
 ref = None
-for env in ({}, {"NXB_ERO_STAGES": "2"}, {"NXB_ERO_STAGES": "3"}, {"NXB_ERO_STAGES": "4"}, {"NXB_ERO_STAGES": "6"}, {"NXB_ERO_STAGES": "8"},
+for env in ({}, {"NXB_ERO_STAGES": "2"}, {"NXB_ERO_STAGES": "4"}, {"NXB_ERO_STAGES": "6"},
             {"NXB_ERO_DIST3": "0"}, {"NXB_ERO_PDL": "0"}, {"NXB_ERO_AFFINE": "0"}, {}):
-    for key in ("NXB_ERO_DIST3", "NXB_ERO_PDL", "NXB_ERO_AFFINE", "NXB_ERO_STAGES", "NXB_ERO_PREFETCH"):
+    for key in ("NXB_ERO_DIST3", "NXB_ERO_PDL", "NXB_ERO_AFFINE", "NXB_ERO_STAGES"):
         os.environ.pop(key, None)
     os.environ.update(env)
     best = 1e9
