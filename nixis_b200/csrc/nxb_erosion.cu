@@ -119,12 +119,38 @@ struct EroPlanArgs {
     EroComm comm;
 };
 
-// erosion.py:210-267 for one vertex, neighbour values already fetched.  PRERAIN: the stored water already
-// holds this sweep's rain (fl(w + rain), added by the previous sweep of the same run when it stored), else
-// it is added here -- the same single rounding either way.
+// erosion.py:210-267 for one vertex, in two steps.
+//
+// Step 1 (ero_slopes), applied to the neighbour values RIGHT WHERE THEY WERE LOADED (inside the branch of
+// the tile kind): dh = hn - me and swq = the neighbour's rained water with the sign of dh.
+//   slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0.
+//     dh > 0: sed_amt += sol * wq, wat_amt += wq * d;   dh < 0: the same with a minus sign;
+//     dh == 0 or NaN: nothing (erosion.py:232-247).
+//   Branch-free: the sign bit of dh is copied onto wq, then two FMAs predicated on dh != 0 -- sol * (+-wq)
+//   and (+-wq) * d are the very products the branchy form contracts to, so results are bit-identical.
+// Why inside the branch: the three tile kinds fetch neighbours differently (shared memory on the hot
+// paths, global gathers on the 0.1 % irregular tiles).  If the raw values merged after the branch, the
+// first instruction behind the merge would wait on the scoreboard of the gathers -- the scoreboard the
+// one-tile-ahead prefetch loads of EVERY tile are in flight on -- and every tile would sit out its own
+// prefetch (63 % of all stall samples of v10's first cut, profiles/r02_erode3_v10_*).
+// PRERAIN: the stored water already holds this sweep's rain (fl(w + rain), added by the previous sweep of
+// the same run when it stored), else it is added here -- the same single rounding either way.
 template <bool PRERAIN>
-__device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i, const float (&hn)[6],
-                                            const float (&wn)[6], const float (&d)[6], float rain,
+__device__ __forceinline__ void ero_slopes(float me, const float (&hn)[6], const float (&wn)[6], float rain,
+                                           float (&dh)[6], float (&swq)[6])
+{
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const float wq = PRERAIN ? wn[q] : wn[q] + rain;
+        dh[q] = hn[q] - me;
+        swq[q] = __uint_as_float(__float_as_uint(wq) ^ (__float_as_uint(dh[q]) & 0x80000000u));
+    }
+}
+
+// Step 2: the accumulation and the deposit rule.
+template <bool PRERAIN>
+__device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i, const float (&dh)[6],
+                                            const float (&swq)[6], const float (&d)[6], float rain,
                                             float &hh, float &ww, float &ss)
 {
     const float evaporation = (float)(0.1 / 320), solubility = (float)(0.01 / 320), capacity = (float)(0.2 / 320);
@@ -132,19 +158,9 @@ __device__ __forceinline__ void erode3_math(float me, float wat_own, float sed_i
     float sed_amt = sed_i, wat_amt = wat_i;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-        const float wq = PRERAIN ? wn[q] : wn[q] + rain;
-        // slope = (hn - me) / (d + 1e-5): only its sign is used and d + 1e-5 > 0.
-        //   dh > 0: sed_amt += sol * wq, wat_amt += wq * d;   dh < 0: the same with a minus sign;
-        //   dh == 0 or NaN: nothing (erosion.py:232-247).
-        // Branch-free: the sign bit of dh is copied onto sol and wq, then two predicated FMAs --
-        // the very FMAs the branchy form contracts to, so results are bit-identical to it.
-        const float dh = hn[q] - me;
-        const uint32_t sgn = __float_as_uint(dh) & 0x80000000u;
-        const float ssol = __uint_as_float(__float_as_uint(solubility) | sgn);
-        const float swq = __uint_as_float(__float_as_uint(wq) ^ sgn);
         asm("{\n\t.reg .pred p;\n\tsetp.ne.f32 p, %2, 0f00000000;\n\t"
-            "@p fma.rn.f32 %0, %3, %4, %0;\n\t@p fma.rn.f32 %1, %5, %6, %1;\n\t}"
-            : "+f"(sed_amt), "+f"(wat_amt) : "f"(dh), "f"(ssol), "f"(wq), "f"(swq), "f"(d[q]));
+            "@p fma.rn.f32 %0, %3, %4, %0;\n\t@p fma.rn.f32 %1, %4, %5, %1;\n\t}"
+            : "+f"(sed_amt), "+f"(wat_amt) : "f"(dh[q]), "f"(solubility), "f"(swq[q]), "f"(d[q]));
     }
     hh = me - sed_amt;
     ss = sed_i + sed_amt;
@@ -202,7 +218,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     __shared__ __align__(8) uint64_t full[ERO_STAGES_MAX], empty[ERO_STAGES_MAX];
     const int n_stages = a.n_stages;
     __shared__ float2 send_hw[COMM ? ERO_TILE : 1];
-    __shared__ bool s_last;
+    __shared__ uint32_t s_last;
     bool cta_sent = false;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -326,27 +342,16 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // dependent descriptor loads: 58 % of all stall samples sat on their first use (profiles/r02_erode3_v8_*).
         // v9: the producer puts the NEXT tile's words into the stage header, the loads for tile it + 1 are
         // issued right after the barrier wait of tile it and are consumed an iteration later.
-        // v10: fewer instructions per vertex (187 -> ~115 warp-instructions on a kind-3 tile): 32-bit vertex
-        // and table indices (one IMAD.WIDE per address), the loop unrolled by two so that the two prefetch
-        // register sets swap roles instead of being copied, water stored already rained.
+        // v10: fewer instructions per vertex (187 -> ~125 warp-instructions on a kind-3 tile): 32-bit vertex
+        // and table indices, water stored already rained, slopes taken where the neighbours are loaded.
         const float *p3 = a.dist3 + 3 * c;
         uint32_t v = blockIdx.x * (uint32_t)ERO_TILE + (uint32_t)c;
         const uint32_t v_step = gridDim.x * (uint32_t)ERO_TILE;
 
-        auto body = [&](const EroPre &cur, EroPre &nxt) {
+        auto body = [&](EroPre &cur) {
             nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
             const EroStage &st = *stp;
             const int kind = st.kind;
-            {
-                const int nmode = st.nmode;
-                if (nmode == ERO_PRE_D3) {
-                    const uint4 o0 = *reinterpret_cast<const uint4 *>(st.nd);
-                    const uint2 o1 = *reinterpret_cast<const uint2 *>(st.nd + 6);
-                    ero_prefetch_d3(a, p3, o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, v + v_step, nxt);
-                } else if (nmode != ERO_PRE_NONE) {
-                    ero_prefetch_row(a, nmode == ERO_PRE_CODES, v + v_step, nxt);
-                }
-            }
             // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
             // at most twice: the row ends next to the mesh skeleton, 20 % of a shard's tiles with ~3 entries
             // each) is handled per thread: every thread scans the tile's entries -- uniform loads -- and keeps
@@ -371,9 +376,10 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     }
                 }
             }
-            float hn[6], wn[6];
+            float dh[6], swq[6];
             float me, wo;
             if (kind != ERO_KIND_CODES) {
+                float hn[6], wn[6];
                 // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
                 const char *hwb = reinterpret_cast<const char *>(st.hw + c);
                 const float2 own = st.hw[c + ERO_WIN_PAD];
@@ -384,13 +390,16 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                              n3 = lds_f32x2_at(hwb, ka.w), n4 = lds_f32x2_at(hwb, kb.x), n5 = lds_f32x2_at(hwb, kb.y);
                 hn[0] = n0.x; wn[0] = n0.y; hn[1] = n1.x; wn[1] = n1.y; hn[2] = n2.x; wn[2] = n2.y;
                 hn[3] = n3.x; wn[3] = n3.y; hn[4] = n4.x; wn[4] = n4.y; hn[5] = n5.x; wn[5] = n5.y;
+                ero_slopes<PRERAIN>(me, hn, wn, a.rain, dh, swq);
             } else {
+                float hn[6], wn[6];
                 const float2 own = st.hw[c];
                 me = own.x; wo = own.y;
                 if (!st.irregular) {
                     const uint32_t code[6] = {cur.c0 & 0xffffu, cur.c0 >> 16, cur.c1 & 0xffffu, cur.c1 >> 16, cur.c2 & 0xffffu, cur.c2 >> 16};
 #pragma unroll
                     for (int q = 0; q < 6; ++q) { const float2 nq = st.hw[code[q] & ERO_CODE_POS]; hn[q] = nq.x; wn[q] = nq.y; }
+                    ero_slopes<PRERAIN>(me, hn, wn, a.rain, dh, swq);
                 } else {
                     // neighbours of this tile are scattered (mesh skeleton, shard seams): global gathers
                     const uint32_t vv = v < n_own ? v : n_own - 1;
@@ -403,12 +412,31 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                         const float2 nq = __ldg(a.hw_in + n);
                         hn[q] = nq.x; wn[q] = nq.y;
                     }
+                    ero_slopes<PRERAIN>(me, hn, wn, a.rain, dh, swq);
+                }
+            }
+            float hh, ww, ss;
+            erode3_math<PRERAIN>(me, wo, cur.so, dh, swq, cur.d, a.rain, hh, ww, ss);
+            // ---- the next tile's per-vertex loads, issued only now that every value prefetched for THIS tile has
+            // been consumed.  All these loads share one hardware scoreboard (a counter: waiting for it waits for
+            // every load in flight on it), so issuing them any earlier makes the first use of this tile's values
+            // wait for the next tile's loads as well -- v10's first cut did exactly that and gained nothing from
+            // prefetching.  From here the loads have the stores, the loop tail and the next tile's barrier wait,
+            // shared-memory reads and slope step to land: about 0.7 of an iteration.
+            // (The next tile's words are read from the stage header here, so the stage is released only now,
+            // ~70 instructions later than strictly necessary: cheaper than carrying seven registers through the math.)
+            {
+                const int nmode = st.nmode;
+                if (nmode == ERO_PRE_D3) {
+                    const uint4 o0 = *reinterpret_cast<const uint4 *>(st.nd);
+                    const uint2 o1 = *reinterpret_cast<const uint2 *>(st.nd + 6);
+                    ero_prefetch_d3(a, p3, o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, v + v_step, cur);
+                } else if (nmode != ERO_PRE_NONE) {
+                    ero_prefetch_row(a, nmode == ERO_PRE_CODES, v + v_step, cur);
                 }
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
-            float hh, ww, ss;
-            erode3_math<PRERAIN>(me, wo, cur.so, hn, wn, cur.d, a.rain, hh, ww, ss);
             if (a.rain_on_store) ww += a.rain;              // the next sweep's `water += rain`, erosion.py:182-183
             if (v < n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
             if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
@@ -431,14 +459,25 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             v += v_step;
         };
 
-        EroPre pa, pb;
-        pa.c0 = pa.c1 = pa.c2 = pb.c0 = pb.c1 = pb.c2 = 0u;
-        if (pmode == ERO_PRE_D3) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pa);
-        else if (pmode != ERO_PRE_NONE) ero_prefetch_row(a, pmode == ERO_PRE_CODES, v, pa);
-        for (uint32_t it = 0; it < my_tiles; it += 2) {
-            body(pa, pb);
-            if (it + 1 < my_tiles) body(pb, pa);
+        // ONE register set: by the time the next tile's loads are issued (behind the math) this tile's values
+        // are dead, so the loads land in the very registers they are read from an iteration later
+        EroPre pre;
+        pre.c0 = pre.c1 = pre.c2 = 0u;
+        if (pmode == ERO_PRE_D3) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pre);
+        else if (pmode != ERO_PRE_NONE) ero_prefetch_row(a, pmode == ERO_PRE_CODES, v, pre);
+        // The first tile's values are LANDED here (one real instruction that reads them all): the loop head is a
+        // merge of this prologue and the back edge, and with loads of the prologue still in flight the compiler
+        // must guard the registers the loop head reuses with a wait on the prefetch scoreboard -- a wait EVERY
+        // tile would then pay right behind its barrier wait.  (The bit pattern is a NaN payload no arithmetic
+        // produces; the store never happens.)
+        {
+            const uint32_t x = __float_as_uint(pre.so) ^ __float_as_uint(pre.d[0]) ^ __float_as_uint(pre.d[1]) ^
+                               __float_as_uint(pre.d[2]) ^ __float_as_uint(pre.d[3]) ^ __float_as_uint(pre.d[4]) ^
+                               __float_as_uint(pre.d[5]) ^ pre.c0 ^ pre.c1 ^ pre.c2;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0x7fd5a3c1;\n\t@p st.shared.u32 [%1], %0;\n\t}"
+                         :: "r"(x), "r"(nxb_smem_u32(&s_last)) : "memory");
         }
+        for (uint32_t it = 0; it < my_tiles; ++it) body(pre);
     }
     if (COMM && a.comm.n_send_peers > 0) {
         // every peer store of this CTA is visible system-wide before the CTA checks in; the last
