@@ -58,14 +58,18 @@
 #define ERO_CONSUMER_WARPS (ERO_TILE / 32)
 #define ERO_THREADS (ERO_TILE + 32)
 
+#define ERO_MAX_PEERS 8
+#define ERO_SEND_SCAN 8           // a tile with more send entries (or a vertex sent more than twice) takes the staged path
+
 struct __align__(128) EroStage {
     float2 hw[ERO_STAGE_ELEMS];         // {height, water}; kind 1: [own tile | halo runs]; kinds 2/3: [window 264 | halo runs]
     // header, written by the producer warp before lane 0 arms the full barrier
     int32_t kind, irregular;
     int32_t nmode;                      // what the consumers prefetch for the CTA's NEXT tile (ERO_PRE_*)
-    int32_t pad0;
+    int32_t send_info;                  // multi-GPU: 0 = this tile sends nothing; sparse tile: n entries | consumer-warp mask << 16; dense tile: 0x100
     int32_t affk8[8];                   // [0..5] kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]; [6], [7]: this tile's send range
     uint32_t nd[8];                     // NEXT tile, kind 3: [0..3], [6], [7] = 3 * v0_next + D_q, q = 0..3, 4, 5 (index into dist3 of the tile's vertex 0)
+    uint2 send[ERO_SEND_SCAN];          // multi-GPU, SPARSE send tile: its entries {dst, c | peer << 16}, staged by the producer warp
 };
 
 // what a consumer thread loads for itself, one tile ahead (nmode of the stage header)
@@ -79,8 +83,6 @@ struct __align__(128) EroStage {
 // iteration later, so neither the descriptor -> length dependency nor DRAM latency is ever waited for).
 struct EroPre { float so; float d[6]; uint32_t c0, c1, c2; };
 
-#define ERO_MAX_PEERS 8
-#define ERO_SEND_SCAN 8           // a tile with more send entries (or a vertex sent more than twice) takes the staged path
 
 // One boundary value this rank owes a peer: vertex `c` of a tile goes to element `dst` (< 2^28) of peer
 // slot `peer`'s output buffer.  Entries are grouped by tile; the tile's range [send0, send1) sits in its
@@ -100,6 +102,11 @@ struct EroComm {
     int n_send_peers;
     uint32_t flag_value;
     unsigned int *ticket;
+    // flags of the PREVIOUS sweep awaited inside this kernel (n_wait = 0: a separate wait kernel ran in front)
+    const uint32_t *wait_flags;         // this rank's flag array (one slot per source rank)
+    const int32_t *wait_ranks;
+    int n_wait;
+    uint32_t wait_target;
 };
 
 struct EroPlanArgs {
@@ -218,7 +225,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     __shared__ __align__(8) uint64_t full[ERO_STAGES_MAX], empty[ERO_STAGES_MAX];
     const int n_stages = a.n_stages;
     __shared__ float2 send_hw[COMM ? ERO_TILE : 1];
-    __shared__ uint32_t s_last;
+    __shared__ uint32_t s_last, s_sent;
     bool cta_sent = false;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -235,10 +242,12 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
 #pragma unroll
         for (int s = 0; s < ERO_STAGES_MAX; ++s) { nxb_mbar_init(&full[s], 1); nxb_mbar_init(&empty[s], ERO_CONSUMER_WARPS); }
         nxb_fence_mbar_init();
+        s_sent = 0u;
     }
     // the plan is constant: the first descriptors are fetched before the previous sweep has drained
     const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
     int32_t word = 0, word_n = 0;               // producer warp: this lane's word of the descriptors of tiles it, it + 1
+    uint2 ent = make_uint2(0u, 0u);             // producer lane e < ERO_SEND_SCAN: entry e of the current tile's sparse send list
     int pmode = ERO_PRE_NONE;                   // consumers: what to load for the CTA's first tile
     uint32_t idx3[6] = {0, 0, 0, 0, 0, 0};
     if (my_tiles > 0) {
@@ -246,6 +255,11 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         if (warp == 0) {
             word = __ldg(tw + lane);
             if (my_tiles > 1) word_n = __ldg(tw + (size_t)gridDim.x * ERO_DESC_WORDS + lane);
+            if (COMM && a.comm.n_send_peers > 0) {
+                const int s0 = __shfl_sync(0xffffffffu, word, ERO_DW_SEND), s1 = __shfl_sync(0xffffffffu, word, ERO_DW_SEND + 1);
+                if (s0 >= 0 && lane < s1 - s0 && lane < ERO_SEND_SCAN)
+                    ent = __ldg(reinterpret_cast<const uint2 *>(a.comm.send_entries) + s0 + lane);
+            }
         } else {
             const int4 f = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_NSEG));        // nseg, irregular, halo_used, d3
             const int aff = (a.use_affine && !f.y) ? __ldg(tw + ERO_DW_AFFINE) : 0;
@@ -261,6 +275,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous sweep's output is complete and visible
+    if (COMM && a.comm.n_wait > 0) {
+        // The peers' boundary values of the previous sweep have landed in this rank's halo slots once their flags
+        // show that sweep's number.  Every CTA checks for itself (one lane per source rank; the flags are in
+        // local memory): no separate wait kernel, one programmatic hand-over per sweep instead of two.
+        if (tid < a.comm.n_wait) {
+            const volatile uint32_t *f = a.comm.wait_flags + a.comm.wait_ranks[tid];
+            while ((int32_t)(*f - a.comm.wait_target) < 0) { __nanosleep(20); }     // flags only grow; wrap-safe
+            __threadfence_system();
+            asm volatile("fence.proxy.async;" ::: "memory");    // the halo slots are read by bulk copies (async proxy)
+        }
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
@@ -295,12 +321,23 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
                       kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
             const int snd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), snd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
+            int send_info = 0;
+            if (COMM && a.comm.n_send_peers > 0 && snd1 > (snd0 < 0 ? -1 - snd0 : snd0)) {
+                if (snd0 < 0) send_info = 0x100;                    // dense: staged path, entries read from global memory
+                else {
+                    // sparse: which consumer warps hold a vertex of the list (the others skip the scan altogether)
+                    const int n = snd1 - snd0;
+                    const uint32_t wbit = lane < n ? 1u << ((ent.y & 0xffffu) >> 5) : 0u;
+                    send_info = n | (int)(__reduce_or_sync(0xffffffffu, wbit) << 16);
+                }
+            }
             nxb_mbar_wait(&empty[s], ph_empty);
             EroStage &st = stage[s];
             // lanes holding D_q of the next tile turn it into the dist3 index of that tile's vertex 0
             if (lane >= ERO_DW_D3OFF) st.nd[lane - ERO_DW_D3OFF] = (uint32_t)nxt + (tile + gridDim.x) * (3u * ERO_TILE);
+            if (COMM && lane < ERO_SEND_SCAN) st.send[lane] = ent;
             if (lane == 0) {
-                st.kind = kind; st.irregular = irregular; st.nmode = nmode;
+                st.kind = kind; st.irregular = irregular; st.nmode = nmode; st.send_info = send_info;
                 st.affk8[0] = (int)(int16_t)(kw0 & 0xffff) * 8; st.affk8[1] = (kw0 >> 16) * 8;
                 st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
                 st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
@@ -323,6 +360,14 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 nxb_bulk_g2s(st.hw + ERO_TILE + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
             }
             __syncwarp();
+            if (COMM && a.comm.n_send_peers > 0) {
+                // the NEXT tile's sparse send entries, one per lane, fetched a tile ahead (the consumers read
+                // them from the stage header: no global load, no dependent latency on their side)
+                const int s0 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND), s1 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND + 1);
+                ent = make_uint2(0u, 0u);
+                if (it + 1 < my_tiles && s0 >= 0 && lane < s1 - s0 && lane < ERO_SEND_SCAN)
+                    ent = __ldg(reinterpret_cast<const uint2 *>(a.comm.send_entries) + s0 + lane);
+            }
             if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
         }
     } else {
@@ -354,27 +399,28 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int kind = st.kind;
             // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
             // at most twice: the row ends next to the mesh skeleton, 20 % of a shard's tiles with ~3 entries
-            // each) is handled per thread: every thread scans the tile's entries -- uniform loads -- and keeps
-            // the (peer, slot) pairs of ITS vertex; after the math it stores its own {h, w} straight to the
-            // peer.  No block barrier, no staging.  (Round 2, first cut: every send tile went through two named
+            // each) is handled per thread: every thread scans the tile's entries -- staged in the stage header by
+            // the producer warp, which fetched them a tile ahead -- and keeps the (peer, slot) pairs of ITS
+            // vertex; after the math it stores its own {h, w} straight to the peer.  No block barrier, no
+            // global load on the consumer side.  (Round 2, first cut: every send tile went through two named
             // barriers and a dependent load, 1.1 us per send tile, +23 us per sweep at 4 GPUs.)  DENSE tiles
             // (seam rows, the skeleton's own tiles) keep the staged path.
-            int32_t e0 = 0, e1 = 0;
             uint32_t snd0 = 0xffffffffu, snd1 = 0xffffffffu;   // (peer << 28) | slot in the peer's buffer
-            bool dense = false;
-            if (COMM && a.comm.n_send_peers > 0) {
-                const int2 sr = *reinterpret_cast<const int2 *>(st.affk8 + 6);
-                dense = sr.x < 0;
-                e0 = dense ? -1 - sr.x : sr.x; e1 = sr.y;
-                if (!dense) {
-                    for (int32_t e = e0; e < e1; ++e) {
-                        const EroSendEntry en = a.comm.send_entries[e];
-                        if (en.c == (uint16_t)c) {
-                            const uint32_t packed = ((uint32_t)en.peer << 28) | (uint32_t)en.dst;
-                            if (snd0 == 0xffffffffu) snd0 = packed; else snd1 = packed;
-                        }
+            const int send_info = COMM ? st.send_info : 0;
+            if (COMM && (send_info >> (15 + warp)) & 1) {       // sparse tile and this warp holds one of its vertices
+                const int n = send_info & 0xff;
+                for (int e = 0; e < n; ++e) {
+                    const uint2 en = st.send[e];                // {dst, c | peer << 16}: shared-memory broadcast
+                    if ((en.y & 0xffffu) == (uint32_t)c) {
+                        const uint32_t packed = ((en.y >> 16) << 28) | en.x;
+                        if (snd0 == 0xffffffffu) snd0 = packed; else snd1 = packed;
                     }
                 }
+            }
+            int32_t e0 = 0, e1 = 0;
+            if (COMM && send_info == 0x100) {                   // dense tile: its range of the global entry list
+                const int2 sr = *reinterpret_cast<const int2 *>(st.affk8 + 6);
+                e0 = -1 - sr.x; e1 = sr.y;
             }
             float dh[6], swq[6];
             float me, wo;
@@ -439,8 +485,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a) : "memory");
             if (a.rain_on_store) ww += a.rain;              // the next sweep's `water += rain`, erosion.py:182-183
             if (v < n_own) { a.hw_out[v] = make_float2(hh, ww); a.s_out[v] = ss; }
-            if (COMM && e1 > e0) {                // uniform over the 8 consumer warps
-                if (!dense) {
+            if (COMM && send_info != 0) {         // uniform over the 8 consumer warps
+                if (send_info != 0x100) {
                     if (snd0 != 0xffffffffu) a.comm.peer_hw[snd0 >> 28][snd0 & 0x0fffffffu] = make_float2(hh, ww);   // one 8-byte store over NVLink
                     if (snd1 != 0xffffffffu) a.comm.peer_hw[snd1 >> 28][snd1 & 0x0fffffffu] = make_float2(hh, ww);
                 } else {
@@ -480,18 +526,22 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         for (uint32_t it = 0; it < my_tiles; ++it) body(pre);
     }
     if (COMM && a.comm.n_send_peers > 0) {
-        // every peer store of this CTA is visible system-wide before the CTA checks in; the last
-        // CTA of the grid then raises this rank's flag in every peer
-        if (cta_sent) __threadfence_system();
+        // Every peer store of this CTA is visible system-wide before the CTA checks in: the consumers' stores
+        // happen-before the CTA barrier, thread 0's system-scope fence behind the barrier is cumulative over
+        // them (ONE fence per CTA; a fence by each of the 288 threads cost ~10 us per sweep).  The last CTA of
+        // the grid then raises this rank's flag in every peer.
+        if (cta_sent) s_sent = 1u;
         __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1);
+        if (tid == 0) {
+            if (s_sent) __threadfence_system();
+            s_last = (atomicAdd(a.comm.ticket, 1u) == gridDim.x - 1);
+        }
         __syncthreads();
         if (s_last) {
             if (tid < a.comm.n_send_peers) {
                 __threadfence_system();
                 volatile uint32_t *f = a.comm.peer_flag[tid];
                 *f = a.comm.flag_value;
-                __threadfence_system();
             }
             if (tid == 0) *a.comm.ticket = 0;
         }
@@ -727,7 +777,7 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
 // Launch side.  The configuration (pipeline depth, grid, environment switches) is resolved once
 // per call, the sweep loop runs here, not in Python.
 struct EroLaunchCfg {
-    int stages, use_affine, use_dist3, pdl;
+    int stages, use_affine, use_dist3, pdl, wait_in_sweep;
     size_t smem;
     int grid[2];                // [COMM]
 };
@@ -747,6 +797,7 @@ static int ero_launch_cfg(int64_t n_own, EroLaunchCfg &cfg)
     cfg.use_affine = env_int("NXB_ERO_AFFINE", 1);          // read per call: tests toggle it
     cfg.use_dist3 = env_int("NXB_ERO_DIST3", 1);
     cfg.pdl = env_int("NXB_ERO_PDL", 1);
+    cfg.wait_in_sweep = env_int("NXB_ERO_WAIT_IN_SWEEP", 1);        // 0: separate one-warp wait kernel in front of every sweep
     cfg.smem = sizeof(EroStage) * cfg.stages;
     int dev = 0;
     NXB_CUDA(cudaGetDevice(&dev));
@@ -867,7 +918,8 @@ NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, co
     EroPlanArgs a;
     if (n_own > 0 && (rc = ero_base_args(a, cfg, plan_mem, adj, dist, dist3, n_own, rain))) return rc;
     for (int64_t i = 0; i < n_sweeps; ++i) {
-        if (n_wait > 0 && (rc = nxb_halo_wait_launch(flags, wait_ranks_dev, n_wait, sweep_base + 1u + (uint32_t)i, cfg.pdl, (cudaStream_t)stream))) return rc;
+        const bool wait_here = n_wait > 0 && (!cfg.wait_in_sweep || n_own == 0);
+        if (wait_here && (rc = nxb_halo_wait_launch(flags, wait_ranks_dev, n_wait, sweep_base + 1u + (uint32_t)i, cfg.pdl, (cudaStream_t)stream))) return rc;
         if (n_own == 0) continue;
         const bool odd = (i & 1) != 0;
         rc = odd ? ero_set_buffers(a, hw_b, s_b, hw_a, s_a) : ero_set_buffers(a, hw_a, s_a, hw_b, s_b);
@@ -882,6 +934,10 @@ NXB_API int nxb_erode3_run_comm_f32(const void *plan_mem, const int32_t *adj, co
             a.comm.n_send_peers = n_send_peers;
             a.comm.ticket = (unsigned int *)ticket;
             a.comm.flag_value = sweep_base + 2u + (uint32_t)i;
+        }
+        if (n_wait > 0 && !wait_here) {
+            a.comm.wait_flags = (const uint32_t *)flags; a.comm.wait_ranks = wait_ranks_dev;
+            a.comm.n_wait = n_wait; a.comm.wait_target = sweep_base + 1u + (uint32_t)i;
         }
         a.rain_on_store = i + 1 < n_sweeps;         // what goes to the peers is what is stored: consistent on every rank
         if ((rc = ero_launch<true>(cfg, a, i > 0, (cudaStream_t)stream))) return rc;

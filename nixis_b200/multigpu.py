@@ -295,8 +295,9 @@ class ShardedErosion:
         self.run(1, rain)
 
     def run(self, n, rain=RAIN_AMOUNT):
-        """n sweeps.  fused transport: ONE call, the loop (flag wait + sweep-with-exchange per sweep,
-        chained with programmatic dependent launch) is issued from C (nxb_erode3_run_comm_f32)."""
+        """n sweeps.  fused transport: ONE call, the loop (one sweep-with-exchange kernel per sweep that first
+        awaits the peers' flags of the previous sweep, chained with programmatic dependent launch) is issued
+        from C (nxb_erode3_run_comm_f32)."""
         if n <= 0:
             return
         if self.transport == "fused" and self.world > 1:
@@ -316,7 +317,7 @@ class ShardedErosion:
                           rt._ptr(self.send_entries), len(self.send_peers), pa[0], pb[0], pa[1],
                           rt._ptr(self.flags), rt._ptr(self.recv_ranks), n_wait,
                           C.c_uint32(self.sweeps), rt._ptr(self.ticket), rt._stream(),
-                          launches=int(n_call) * (2 if n_wait else 1))
+                          launches=int(n_call) * (2 if (n_wait and os.environ.get("NXB_ERO_WAIT_IN_SWEEP", "1") == "0") else 1))
                 self._pending = True
                 if n_call % 2:
                     self.cur = 1 - self.cur

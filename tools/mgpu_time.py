@@ -67,8 +67,8 @@ for cost in os.environ.get("MGPU_COSTS", "6").split(","):
             print(f"  {label}: per rank {[round(x[0], 1) for x in t]} us/sweep", flush=True)
         dist.barrier()
     ero.sweeps = (1 << 20) + 400          # keep the flag values monotone for the real loop below
-    for env in ({}, {"NXB_ERO_PDL": "0"}):
-        for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT"):
+    for env in ({}, {"NXB_ERO_WAIT_IN_SWEEP": "0"}, {"NXB_ERO_PDL": "0"}):
+        for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT", "NXB_ERO_WAIT_IN_SWEEP"):
             os.environ.pop(key, None)
         os.environ.update(env)
         ero.wait_mode = os.environ.get("NXB_HALO_WAIT", "kernel")
@@ -83,7 +83,7 @@ for cost in os.environ.get("MGPU_COSTS", "6").split(","):
             best = min(best, ms.item() / 300 * 1e3)
         if rank == 0:
             print(f"  exchanging loop {str(env):28s} {best:.1f} us/sweep (max over ranks)", flush=True)
-    for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT"):
+    for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT", "NXB_ERO_WAIT_IN_SWEEP"):
         os.environ.pop(key, None)
     ero.close()
     del terr, ero

@@ -1,4 +1,5 @@
-"""Tiny driver for ncu captures: python tools/prof_driver.py {fbm|erode3|erode1|assembly} [k] [launches]"""
+"""Tiny driver for ncu captures: python tools/prof_driver.py {fbm|erode3|erode3comm|erode1|assembly} [k] [launches]
+(erode3comm: the exchange-capable instantiation of the sweep, no peers, on one GPU)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,6 +24,25 @@ else:
     st = pipe.erosion_state(h.clone())
     if what == "erode3":
         st.run(n)
+    elif what == "erode3comm":
+        import ctypes as C
+        from nixis_b200 import _lib
+        tp = pipe._plan
+        ticket = torch.zeros(4, dtype=torch.int32, device="cuda")
+        a, b = st.cur, st.nxt
+        d3 = tp.dist3_for(st.dist)
+        for rep in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("nxb_erode3_run_comm_f32", rt._ptr(tp.mem), rt._ptr(tp.adj), rt._ptr(st.dist), None if d3 is None else rt._ptr(d3),
+                      rt._ptr(a[0]), rt._ptr(a[1]), rt._ptr(b[0]), rt._ptr(b[1]),
+                      tp.n_own, C.c_float(0.3 / 320), n, None, 0, None, None, None, None, None, 0,
+                      C.c_uint32(0), rt._ptr(ticket), rt._stream())
+            e1.record(); torch.cuda.synchronize()
+            print("erode3comm", k, n, "sweeps:", e0.elapsed_time(e1) / n * 1e3, "us/sweep")
+            e0.record(); st.run(n); e1.record(); torch.cuda.synchronize()
+            print("erode3    ", k, n, "sweeps:", e0.elapsed_time(e1) / n * 1e3, "us/sweep")
     else:
         a, b = st.cur[0], torch.empty_like(st.cur[0])
         for _ in range(n):
