@@ -279,11 +279,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // The peers' boundary values of the previous sweep have landed in this rank's halo slots once their flags
         // show that sweep's number.  Every CTA checks for itself (one lane per source rank; the flags are in
         // local memory): no separate wait kernel, one programmatic hand-over per sweep instead of two.
-        if (tid < a.comm.n_wait) {
-            const volatile uint32_t *f = a.comm.wait_flags + a.comm.wait_ranks[tid];
-            while ((int32_t)(*f - a.comm.wait_target) < 0) { __nanosleep(20); }     // flags only grow; wrap-safe
-            __threadfence_system();
-            asm volatile("fence.proxy.async;" ::: "memory");    // the halo slots are read by bulk copies (async proxy)
+        if (warp == 0) {
+            if (lane < a.comm.n_wait) {
+                const uint32_t *f = a.comm.wait_flags + a.comm.wait_ranks[lane];
+                uint32_t seen;
+                for (;;) {                      // acquire at system scope: no full memory barrier per poll or per CTA
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                    if ((int32_t)(seen - a.comm.wait_target) >= 0) break;   // flags only grow; wrap-safe
+                    __nanosleep(32);
+                }
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");    // the halo slots are read by this warp's bulk copies (async proxy)
         }
         __syncthreads();
     }
@@ -321,6 +328,15 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int kw0 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK), kw1 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 1),
                       kw2 = __shfl_sync(0xffffffffu, cur, ERO_DW_AFFK + 2);
             const int snd0 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND), snd1 = __shfl_sync(0xffffffffu, cur, ERO_DW_SEND + 1);
+            // the NEXT tile's sparse send entries, one per lane, requested NOW and written into the next stage header
+            // an iteration later (the consumers read them from shared memory: no global load on their side, and
+            // none the producer has to sit out between two tiles either)
+            uint2 ent_n = make_uint2(0u, 0u);
+            if (COMM && a.comm.n_send_peers > 0) {
+                const int s0 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND), s1 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND + 1);
+                if (it + 1 < my_tiles && s0 >= 0 && lane < s1 - s0 && lane < ERO_SEND_SCAN)
+                    ent_n = __ldg(reinterpret_cast<const uint2 *>(a.comm.send_entries) + s0 + lane);
+            }
             int send_info = 0;
             if (COMM && a.comm.n_send_peers > 0 && snd1 > (snd0 < 0 ? -1 - snd0 : snd0)) {
                 if (snd0 < 0) send_info = 0x100;                    // dense: staged path, entries read from global memory
@@ -360,14 +376,7 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 nxb_bulk_g2s(st.hw + ERO_TILE + seg_off, a.hw_in + seg_start, seg_len * 8u, &full[s]);
             }
             __syncwarp();
-            if (COMM && a.comm.n_send_peers > 0) {
-                // the NEXT tile's sparse send entries, one per lane, fetched a tile ahead (the consumers read
-                // them from the stage header: no global load, no dependent latency on their side)
-                const int s0 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND), s1 = __shfl_sync(0xffffffffu, nxt, ERO_DW_SEND + 1);
-                ent = make_uint2(0u, 0u);
-                if (it + 1 < my_tiles && s0 >= 0 && lane < s1 - s0 && lane < ERO_SEND_SCAN)
-                    ent = __ldg(reinterpret_cast<const uint2 *>(a.comm.send_entries) + s0 + lane);
-            }
+            ent = ent_n;
             if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
         }
     } else {

@@ -66,6 +66,13 @@ for cost in os.environ.get("MGPU_COSTS", "6").split(","):
         if rank == 0:
             print(f"  {label}: per rank {[round(x[0], 1) for x in t]} us/sweep", flush=True)
         dist.barrier()
+    # compute-only once more (the GPUs run at their power cap: is a later measurement slower by itself?)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = ev(), ev()
+    e0.record(); rt.erode3_run(tp, ero.dist, a, b, 0.0, 200); e1.record(); torch.cuda.synchronize()
+    t = gather([e0.elapsed_time(e1) / 200 * 1e3])
+    if rank == 0:
+        print(f"  compute-only again, after the COMM runs: per rank {[round(x[0], 1) for x in t]} us/sweep", flush=True)
     ero.sweeps = (1 << 20) + 400          # keep the flag values monotone for the real loop below
     for env in ({}, {"NXB_ERO_WAIT_IN_SWEEP": "0"}, {"NXB_ERO_PDL": "0"}):
         for key in ("NXB_ERO_PDL", "NXB_HALO_WAIT", "NXB_ERO_WAIT_IN_SWEEP"):
