@@ -143,8 +143,18 @@ def _erode_terrain3_sharded(ctx, nodes, neighbors, heights, num_iter, return_sta
     fetched once for the edge lengths, then the sharded sweep loop with the fused exchange."""
     from .multigpu import ShardedErosion
     from .partition import build_rank_plan_local, exchange_halo_torch
+    import os, time
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):                     # NXB_TIMING=1: where the call's time goes (tools/e2e_probe.py)
+        if os.environ.get("NXB_TIMING"):
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
     rows = _neighbors(neighbors)
+    mark("upload rows")
     plan = build_rank_plan_local(rows, ctx.rank, ctx.world, ctx.ranges, group=ctx.group)
+    mark("halo plan")
     own64 = nodes if isinstance(nodes, torch.Tensor) else rt.upload(np.ascontiguousarray(nodes, dtype=np.float64))
     assert own64.dtype == torch.float64 and own64.shape == (plan.n_own, 3), "nodes must be this rank's float64 [n_own,3] slice"
     comps = []
@@ -152,23 +162,37 @@ def _erode_terrain3_sharded(ctx, nodes, neighbors, heights, num_iter, return_sta
         c = torch.zeros(plan.capacity, dtype=torch.float64, device=own64.device)
         c[: plan.n_own] = own64[:, a]
         comps.append(c)
+    mark("upload positions")
     exchange_halo_torch(plan, comps, group=ctx.group)
+    mark("halo positions")
     dist_f32 = rt.edge_lengths(torch.stack(comps, dim=1).contiguous(), plan.local_adj)
     del comps
+    mark("edge lengths")
     ero = ShardedErosion(plan, dist_f32, transport="fused", group=ctx.group)
+    mark("tile plan + peer memory")
     dev_io = isinstance(heights, torch.Tensor)
     ero.load(heights if dev_io else rt.upload_f32(heights))
+    mark("upload heights + publish")
     ero.run(num_iter)
     ero.finish()
+    mark("sweeps")
+
+    def report():
+        if os.environ.get("NXB_TIMING"):
+            print(f"  erode_terrain3 (sharded, rank {ctx.rank}): " +
+                  ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms" for a, b in zip(marks, marks[1:])), flush=True)
     try:
         if dev_io:
             return (ero.heights.clone(), ero.water.clone(), ero.sediment.clone()) if return_state else ero.heights.clone()
         rt.download_f64(ero.heights.contiguous(), out=heights)
+        mark("download")
         if return_state:
             return rt.download_f64(ero.water.contiguous()), rt.download_f64(ero.sediment.contiguous())
         return None
     finally:
         ero.close()
+        mark("close")
+        report()
 
 
 def erode_terrain3(nodes, neighbors, heights, num_iter=1, snapshot=False, verbose=True, return_state=False, exact=False):

@@ -97,6 +97,13 @@ class PeerMemory:
         self._own = None
 
 
+# Symmetric-memory buffers of closed ShardedErosion objects, kept for the next one of the same size: tearing a
+# torch symmetric-memory allocation down costs 0.1 - 1 s (measured, tools/e2e_probe.py), which a caller of the
+# numpy API would pay on EVERY erode_terrain3 call.  Every rank runs the same sequence of constructions with the
+# same (all-reduced) size, so all ranks hit or miss together.
+_PEER_POOL = {}
+
+
 def _is_gloo(group):
     try:
         return dist.get_backend(group) == "gloo"
@@ -142,7 +149,12 @@ class ShardedErosion:
             kinds = [os.environ.get("NXB_PEER_MEM")] if os.environ.get("NXB_PEER_MEM") else \
                     (["ipc"] if _is_gloo(group) else ["symm", "ipc"])
             err = None
-            for kind in kinds:
+            self._pool_key = ("symm", n_state + MAX_FLAGS, str(dev), id(group))
+            pooled = _PEER_POOL.pop(self._pool_key, None) if kinds[0] == "symm" else None
+            if pooled is not None:
+                pooled.buf.zero_()                  # flags and state of the previous user; everybody zeroes before the barrier below
+                self.peer_mem = pooled
+            for kind in ([] if pooled is not None else kinds):
                 try:
                     self.peer_mem = PeerMemory(n_state + MAX_FLAGS, dev, group, kind)
                     break
@@ -197,8 +209,16 @@ class ShardedErosion:
 
     def close(self):
         if self.peer_mem is not None:
+            if self.peer_mem.kind == "symm":
+                if self._pending:
+                    self._await()               # nobody may still be writing into this buffer
+                self._barrier()
             self.hw = self.flags = self._buf = None
-            self.peer_mem.close()
+            if self.peer_mem.kind == "symm":
+                _PEER_POOL.clear()              # keep one buffer
+                _PEER_POOL[self._pool_key] = self.peer_mem
+            else:
+                self.peer_mem.close()
             self.peer_mem = None
 
     def _build_send_table(self):
