@@ -425,7 +425,7 @@ def run_ours(args):
                 "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_VERT_ITER * V, "avg_launch_ms": ero_launch_ms,
                 "tiles": {"total": plan.n_tiles, "irregular": plan.n_irregular, "affine": plan.n_affine,
-                          "affine_one_length_per_edge": plan.n_affine3},
+                          "affine_one_length_per_edge": plan.n_affine3, "two_piece": plan.n_two},
                 "note": "achieved keeps SURVEY 8d's 60 B per vertex-iteration as numerator; the kernel itself moves "
                         "less (36 B on affine tiles with one stored length per edge, 48 B on other affine tiles: see "
                         "traffic), so frac may exceed 1"}

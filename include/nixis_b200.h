@@ -203,9 +203,10 @@ int nxb_mesh_icosa_edge_lengths(int k, const int32_t *adj_rows, int64_t v_begin,
  * adj: int32[n_own][6] with indices in [0, capacity) (own vertices first, then halo slots of a
  * multi-GPU shard).  capacity = allocated ELEMENTS of every h/w/s buffer later passed to the step
  * (multiple of 256, >= round_up(n_own, 256)).  plan_mem: nxb_erode_plan_bytes(n_own) bytes, 16-byte
- * aligned.  stats_host (nullable) int32[5]: tiles, irregular tiles, max halo slots, affine tiles
+ * aligned.  stats_host (nullable) int32[6]: tiles, irregular tiles, max halo slots, affine tiles
  * (implicit adjacency: the sweep reads no adjacency codes for them), affine tiles that also qualify
- * for one stored length per edge.  Synchronous. */
+ * for one stored length per edge, two-piece tiles (a mesh-row end inside the tile: two sets of
+ * constants + 4 exception vertices).  Synchronous. */
 int64_t nxb_erode_plan_bytes(int64_t n_own);
 int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capacity, void *plan_mem,
                          int32_t *stats_host, void *stream);

@@ -97,6 +97,16 @@ __device__ __forceinline__ void nxb_mbar_wait_a(uint32_t bar_addr, uint32_t pari
                      : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     } while (!ok);
 }
+// the same with a suspend-time hint (ns): the hardware parks the warp until the phase completes or the time is up,
+// instead of returning to a poll loop that competes for issue slots with the warps that still have work
+__device__ __forceinline__ void nxb_mbar_wait_hint(uint32_t bar_addr, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(ns) : "memory");
+    } while (!ok);
+}
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completes on `bar`
 __device__ __forceinline__ void nxb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -68,7 +68,11 @@ struct __align__(128) EroStage {
     int32_t nmode;                      // what the consumers prefetch for the CTA's NEXT tile (ERO_PRE_*)
     int32_t send_info;                  // multi-GPU: 0 = this tile sends nothing; sparse tile: n entries | consumer-warp mask << 16; dense tile: 0x100
     int32_t affk8[8];                   // [0..5] kinds 2/3: byte offset of slot q's neighbour relative to &hw[c]; [6], [7]: this tile's send range
-    uint32_t nd[8];                     // NEXT tile, kind 3: [0..3], [6], [7] = 3 * v0_next + D_q, q = 0..3, 4, 5 (index into dist3 of the tile's vertex 0)
+    uint32_t nd[8];                     // NEXT tile, kinds 3 / 4: [0..3], [6], [7] = 3 * v0_next + D_q, q = 0..3, 4, 5 (index into dist3 of the tile's vertex 0)
+    int32_t affkB8[6];                  // kind 4: the K_q of piece B (c >= split + ERO_EXC)
+    int32_t split, nsplit;              // kind 4: first exception vertex of THIS tile / of the NEXT tile
+    uint32_t ndB[6];                    // NEXT tile, kind 4: 3 * v0_next + D_q of piece B
+    int32_t pad1[2];
     uint2 send[ERO_SEND_SCAN];          // multi-GPU, SPARSE send tile: its entries {dst, c | peer << 16}, staged by the producer warp
 };
 
@@ -77,6 +81,7 @@ struct __align__(128) EroStage {
 #define ERO_PRE_CODES 1                 // full row of six lengths + the 16-bit neighbour codes (kind 1, regular)
 #define ERO_PRE_ROW 2                   // full row of six lengths (kind 2, irregular tiles)
 #define ERO_PRE_D3 3                    // six entries of the one-length-per-edge table (kind 3)
+#define ERO_PRE_TWO 4                   // kind 4: ERO_PRE_D3 with the constants of the vertex's piece; the exception vertices ERO_PRE_CODES
 
 // A vertex's own per-sweep data, loaded straight from global memory ONE TILE AHEAD of its use (the
 // loads are issued right after the barrier wait of the previous tile of this CTA and are consumed an
@@ -115,6 +120,8 @@ struct EroPlanArgs {
     const float *dist;                                  // full table [.][6]
     const float *dist3;                                 // one entry per edge [.][3] (null: full table only)
     int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
+    int use_two;                                        // honour the plan's two-piece tiles (kind 4; needs dist3)
+    int wait_hint_ns;                                   // consumers' barrier wait: suspend-time hint (0: plain poll loop)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
     const float2 *hw_in;                                // {height, water} interleaved: ONE bulk copy per run
     const float *s_in;
@@ -247,14 +254,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
     // the plan is constant: the first descriptors are fetched before the previous sweep has drained
     const int32_t *dw = reinterpret_cast<const int32_t *>(a.desc);
     int32_t word = 0, word_n = 0;               // producer warp: this lane's word of the descriptors of tiles it, it + 1
+    int32_t whi = 0, whi_n = 0;                 // ... and of their second halves (two-piece constants)
+    int psplit = 0;                             // consumers: first exception vertex of the CTA's first tile (kind 4)
+    uint32_t idx3B[6] = {0, 0, 0, 0, 0, 0};
+    const bool two_on = a.use_two && a.use_affine && d3_on;
     uint2 ent = make_uint2(0u, 0u);             // producer lane e < ERO_SEND_SCAN: entry e of the current tile's sparse send list
     int pmode = ERO_PRE_NONE;                   // consumers: what to load for the CTA's first tile
     uint32_t idx3[6] = {0, 0, 0, 0, 0, 0};
     if (my_tiles > 0) {
         const int32_t *tw = dw + (size_t)blockIdx.x * ERO_DESC_WORDS;
         if (warp == 0) {
-            word = __ldg(tw + lane);
-            if (my_tiles > 1) word_n = __ldg(tw + (size_t)gridDim.x * ERO_DESC_WORDS + lane);
+            word = __ldg(tw + lane); whi = __ldg(tw + 32 + lane);
+            if (my_tiles > 1) { word_n = __ldg(tw + (size_t)gridDim.x * ERO_DESC_WORDS + lane); whi_n = __ldg(tw + (size_t)gridDim.x * ERO_DESC_WORDS + 32 + lane); }
             if (COMM && a.comm.n_send_peers > 0) {
                 const int s0 = __shfl_sync(0xffffffffu, word, ERO_DW_SEND), s1 = __shfl_sync(0xffffffffu, word, ERO_DW_SEND + 1);
                 if (s0 >= 0 && lane < s1 - s0 && lane < ERO_SEND_SCAN)
@@ -264,7 +275,15 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const int4 f = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_NSEG));        // nseg, irregular, halo_used, d3
             const int aff = (a.use_affine && !f.y) ? __ldg(tw + ERO_DW_AFFINE) : 0;
             pmode = (aff && d3_on && (f.w & 1)) ? ERO_PRE_D3 : ((aff || f.y) ? ERO_PRE_ROW : ERO_PRE_CODES);
-            if (pmode == ERO_PRE_D3) {
+            if (pmode == ERO_PRE_CODES && two_on && __ldg(tw + ERO_DW_TWO)) {
+                pmode = ERO_PRE_TWO;
+                psplit = __ldg(tw + ERO_DW_SPLIT);
+                const int2 b0 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFFB + 1)), b1 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFFB + 3));
+                const uint32_t b3 = blockIdx.x * (3u * ERO_TILE);
+                idx3B[0] = b3 + (uint32_t)__ldg(tw + ERO_DW_D3OFFB); idx3B[1] = b3 + (uint32_t)b0.x; idx3B[2] = b3 + (uint32_t)b0.y;
+                idx3B[3] = b3 + (uint32_t)b1.x; idx3B[4] = b3 + (uint32_t)b1.y; idx3B[5] = b3 + (uint32_t)__ldg(tw + ERO_DW_D3OFFB + 5);
+            }
+            if (pmode == ERO_PRE_D3 || pmode == ERO_PRE_TWO) {
                 const int4 o0 = __ldg(reinterpret_cast<const int4 *>(tw + ERO_DW_D3OFF));
                 const int2 o1 = __ldg(reinterpret_cast<const int2 *>(tw + ERO_DW_D3OFF45));
                 const uint32_t b3 = blockIdx.x * (3u * ERO_TILE);
@@ -303,20 +322,27 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             const size_t v0 = (size_t)tile * ERO_TILE;
             const int32_t cur = word, nxt = word_n;     // descriptor words: see ERO_DW_*
-            word = word_n;
+            const int32_t cur_hi = whi, nxt_hi = whi_n;
+            word = word_n; whi = whi_n;
             word_n = (it + 2 < my_tiles) ? __ldg(dw + ((size_t)tile + 2 * (size_t)gridDim.x) * ERO_DESC_WORDS + lane) : 0;
+            whi_n = (it + 2 < my_tiles) ? __ldg(dw + ((size_t)tile + 2 * (size_t)gridDim.x) * ERO_DESC_WORDS + 32 + lane) : 0;
             const int nseg = __shfl_sync(0xffffffffu, cur, ERO_DW_NSEG);
             const int irregular = __shfl_sync(0xffffffffu, cur, ERO_DW_IRREGULAR);
             const int halo_used = __shfl_sync(0xffffffffu, cur, ERO_DW_HALO_USED);
             const int d3word = __shfl_sync(0xffffffffu, cur, ERO_DW_D3);
             const int affine = (a.use_affine && !irregular) ? __shfl_sync(0xffffffffu, cur, ERO_DW_AFFINE) : 0;
-            const int kind = !affine ? ERO_KIND_CODES : ((d3_on && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE);
+            const int two = (two_on && !irregular && !affine) ? __shfl_sync(0xffffffffu, cur_hi, ERO_DW_TWO - 32) : 0;
+            const int kind = two ? ERO_KIND_TWO : (!affine ? ERO_KIND_CODES : ((d3_on && (d3word & 1)) ? ERO_KIND_AFFINE3 : ERO_KIND_AFFINE));
             // what the consumers load for themselves for the NEXT tile while they work on this one
             const int irr_n = __shfl_sync(0xffffffffu, nxt, ERO_DW_IRREGULAR);
             const int aff_n = (a.use_affine && !irr_n) ? __shfl_sync(0xffffffffu, nxt, ERO_DW_AFFINE) : 0;
             const int d3_n = __shfl_sync(0xffffffffu, nxt, ERO_DW_D3);
+            const int two_n = (two_on && !irr_n && !aff_n) ? __shfl_sync(0xffffffffu, nxt_hi, ERO_DW_TWO - 32) : 0;
             const int nmode = it + 1 >= my_tiles ? ERO_PRE_NONE
-                              : ((aff_n && d3_on && (d3_n & 1)) ? ERO_PRE_D3 : ((aff_n || irr_n) ? ERO_PRE_ROW : ERO_PRE_CODES));
+                              : (two_n ? ERO_PRE_TWO : ((aff_n && d3_on && (d3_n & 1)) ? ERO_PRE_D3 : ((aff_n || irr_n) ? ERO_PRE_ROW : ERO_PRE_CODES)));
+            const int split = __shfl_sync(0xffffffffu, cur_hi, ERO_DW_SPLIT - 32), split_n = __shfl_sync(0xffffffffu, nxt_hi, ERO_DW_SPLIT - 32);
+            const int kb0 = __shfl_sync(0xffffffffu, cur_hi, ERO_DW_AFFKB - 32), kb1 = __shfl_sync(0xffffffffu, cur_hi, ERO_DW_AFFKB - 31),
+                      kb2 = __shfl_sync(0xffffffffu, cur_hi, ERO_DW_AFFKB - 30);
             const int q = lane - 1;             // segment handled by this lane
             const int qq = q < 0 ? 0 : (q >= ERO_NSEG ? ERO_NSEG - 1 : q);
             const int32_t seg_start = __shfl_sync(0xffffffffu, cur, qq);
@@ -351,6 +377,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             EroStage &st = stage[s];
             // lanes holding D_q of the next tile turn it into the dist3 index of that tile's vertex 0
             if (lane >= ERO_DW_D3OFF) st.nd[lane - ERO_DW_D3OFF] = (uint32_t)nxt + (tile + gridDim.x) * (3u * ERO_TILE);
+            if (lane >= ERO_DW_D3OFFB - 32 && lane < ERO_DW_D3OFFB - 32 + 6)
+                st.ndB[lane - (ERO_DW_D3OFFB - 32)] = (uint32_t)nxt_hi + (tile + gridDim.x) * (3u * ERO_TILE);
             if (COMM && lane < ERO_SEND_SCAN) st.send[lane] = ent;
             if (lane == 0) {
                 st.kind = kind; st.irregular = irregular; st.nmode = nmode; st.send_info = send_info;
@@ -358,6 +386,10 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 st.affk8[2] = (int)(int16_t)(kw1 & 0xffff) * 8; st.affk8[3] = (kw1 >> 16) * 8;
                 st.affk8[4] = (int)(int16_t)(kw2 & 0xffff) * 8; st.affk8[5] = (kw2 >> 16) * 8;
                 st.affk8[6] = snd0; st.affk8[7] = snd1;
+                st.affkB8[0] = (int)(int16_t)(kb0 & 0xffff) * 8; st.affkB8[1] = (kb0 >> 16) * 8;
+                st.affkB8[2] = (int)(int16_t)(kb1 & 0xffff) * 8; st.affkB8[3] = (kb1 >> 16) * 8;
+                st.affkB8[4] = (int)(int16_t)(kb2 & 0xffff) * 8; st.affkB8[5] = (kb2 >> 16) * 8;
+                st.split = split; st.nsplit = split_n;
             }
             __syncwarp();                       // the whole header is written before lane 0 arms the barrier
             if (kind != ERO_KIND_CODES) {
@@ -403,7 +435,8 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         const uint32_t v_step = gridDim.x * (uint32_t)ERO_TILE;
 
         auto body = [&](EroPre &cur) {
-            nxb_mbar_wait_a(full_a, ph_full);   // (sleeping between polls lowers power, not time: measured, dropped)
+            if (a.wait_hint_ns) nxb_mbar_wait_hint(full_a, ph_full, (uint32_t)a.wait_hint_ns);
+            else nxb_mbar_wait_a(full_a, ph_full);
             const EroStage &st = *stp;
             const int kind = st.kind;
             // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
@@ -433,7 +466,33 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             }
             float dh[6], swq[6];
             float me, wo;
-            if (kind != ERO_KIND_CODES) {
+            if (kind == ERO_KIND_TWO) {
+                // two-piece tile: window layout; K_q of the vertex's piece, the ERO_EXC vertices at the row end
+                // through their explicit codes (which address the [own | halo] layout: + 4 / + 8 in the window layout)
+                float hn[6], wn[6];
+                const float2 own = st.hw[c + ERO_WIN_PAD];
+                me = own.x; wo = own.y;
+                const int split = st.split;
+                if ((uint32_t)(c - split) < (uint32_t)ERO_EXC) {
+                    const uint32_t code[6] = {cur.c0 & 0xffffu, cur.c0 >> 16, cur.c1 & 0xffffu, cur.c1 >> 16, cur.c2 & 0xffffu, cur.c2 >> 16};
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        const uint32_t pos = code[q] & ERO_CODE_POS;
+                        const float2 nq = st.hw[pos + (pos >= ERO_TILE ? 2 * ERO_WIN_PAD : ERO_WIN_PAD)];
+                        hn[q] = nq.x; wn[q] = nq.y;
+                    }
+                } else {
+                    const char *hwb = reinterpret_cast<const char *>(st.hw + c);
+                    const int32_t *kk = c < split ? st.affk8 : st.affkB8;
+                    const int2 k01 = *reinterpret_cast<const int2 *>(kk), k23 = *reinterpret_cast<const int2 *>(kk + 2),
+                               k45 = *reinterpret_cast<const int2 *>(kk + 4);
+                    const float2 n0 = lds_f32x2_at(hwb, k01.x), n1 = lds_f32x2_at(hwb, k01.y), n2 = lds_f32x2_at(hwb, k23.x),
+                                 n3 = lds_f32x2_at(hwb, k23.y), n4 = lds_f32x2_at(hwb, k45.x), n5 = lds_f32x2_at(hwb, k45.y);
+                    hn[0] = n0.x; wn[0] = n0.y; hn[1] = n1.x; wn[1] = n1.y; hn[2] = n2.x; wn[2] = n2.y;
+                    hn[3] = n3.x; wn[3] = n3.y; hn[4] = n4.x; wn[4] = n4.y; hn[5] = n5.x; wn[5] = n5.y;
+                }
+                ero_slopes<PRERAIN>(me, hn, wn, a.rain, dh, swq);
+            } else if (kind != ERO_KIND_CODES) {
                 float hn[6], wn[6];
                 // implicit adjacency: slot q's neighbour is at a per-tile constant distance from c
                 const char *hwb = reinterpret_cast<const char *>(st.hw + c);
@@ -486,6 +545,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     const uint4 o0 = *reinterpret_cast<const uint4 *>(st.nd);
                     const uint2 o1 = *reinterpret_cast<const uint2 *>(st.nd + 6);
                     ero_prefetch_d3(a, p3, o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, v + v_step, cur);
+                } else if (nmode == ERO_PRE_TWO) {
+                    const int ns = st.nsplit;
+                    if ((uint32_t)(c - ns) < (uint32_t)ERO_EXC) ero_prefetch_row(a, true, v + v_step, cur);
+                    else if (c < ns) {
+                        const uint4 o0 = *reinterpret_cast<const uint4 *>(st.nd);
+                        const uint2 o1 = *reinterpret_cast<const uint2 *>(st.nd + 6);
+                        ero_prefetch_d3(a, p3, o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, v + v_step, cur);
+                    } else {
+                        const uint2 o0 = *reinterpret_cast<const uint2 *>(st.ndB), o1 = *reinterpret_cast<const uint2 *>(st.ndB + 2),
+                                    o2 = *reinterpret_cast<const uint2 *>(st.ndB + 4);
+                        ero_prefetch_d3(a, p3, o0.x, o0.y, o1.x, o1.y, o2.x, o2.y, v + v_step, cur);
+                    }
                 } else if (nmode != ERO_PRE_NONE) {
                     ero_prefetch_row(a, nmode == ERO_PRE_CODES, v + v_step, cur);
                 }
@@ -518,7 +589,11 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // are dead, so the loads land in the very registers they are read from an iteration later
         EroPre pre;
         pre.c0 = pre.c1 = pre.c2 = 0u;
-        if (pmode == ERO_PRE_D3) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pre);
+        if (pmode == ERO_PRE_TWO) {
+            if ((uint32_t)(c - psplit) < (uint32_t)ERO_EXC) ero_prefetch_row(a, true, v, pre);
+            else if (c < psplit) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pre);
+            else ero_prefetch_d3(a, p3, idx3B[0], idx3B[1], idx3B[2], idx3B[3], idx3B[4], idx3B[5], v, pre);
+        } else if (pmode == ERO_PRE_D3) ero_prefetch_d3(a, p3, idx3[0], idx3[1], idx3[2], idx3[3], idx3[4], idx3[5], v, pre);
         else if (pmode != ERO_PRE_NONE) ero_prefetch_row(a, pmode == ERO_PRE_CODES, v, pre);
         // The first tile's values are LANDED here (one real instruction that reads them all): the loop head is a
         // merge of this prologue and the back edge, and with loads of the prologue still in flight the compiler
@@ -638,70 +713,72 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         d.nseg = k + 1;
     }
     // ---- implicit adjacency: is the staging index of every slot's neighbour c + K_q for all c? ----
-    __shared__ int k0[6];
-    int kq[6];
-    int all_ok;
+    // ---- one length per edge (kind 3): slot q's length of vertex v is dist3[3 v + D_q] ----
+    //   forward slot (neighbour index > v): own row, entry = rank among v's forward slots        D_q = entry
+    //   backward slot: the neighbour's row, entry = rank of v among ITS forward slots            D_q = 3 (n - v) + entry
+    // A tile is kind 3 when K_q and D_q are the same for all 256 vertices and nobody has more than 3 forward
+    // neighbours (rows with more -- mesh skeleton, shard seams -- keep only their first 3 lengths in dist3 and
+    // must never be referenced); kind 4 (two-piece) when that holds separately for the vertices in front of and
+    // behind a window of ERO_EXC exception vertices (the end of a mesh row inside the tile).
+    __shared__ int k0[6], j0[6], k1[6], j1[6];
+    int kq[6], jq[6];
+    const bool tile_ok = !d.irregular && v0 + ERO_TILE <= n_own && v0 >= ERO_WIN_PAD && v0 + ERO_TILE + ERO_WIN_PAD <= capacity &&
+                         ERO_WIN + d.halo_used <= ERO_STAGE_ELEMS;
+    bool vk_ok = tile_ok, vd_ok = tile_ok;          // this vertex fits the implicit / one-length-per-edge scheme at all
     {
-        bool ok = !d.irregular && v < n_own && v0 >= ERO_WIN_PAD && v0 + ERO_TILE + ERO_WIN_PAD <= capacity &&
-                  ERO_WIN + d.halo_used <= ERO_STAGE_ELEMS;
+        int fcnt = 0;
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
             const int64_t n = nb[q];
-            if (n < 0) { ok = false; kq[q] = 0; continue; }
+            kq[q] = 0; jq[q] = 0;
+            if (!tile_ok) continue;
+            if (n < 0) { vk_ok = false; vd_ok = false; continue; }
             int widx;
             if (n >= v0 - ERO_WIN_PAD && n < v0 + ERO_TILE + ERO_WIN_PAD) widx = (int)(n - v0) + ERO_WIN_PAD;
             else widx = ERO_WIN + ((int)(code[q] & ERO_CODE_POS) - ERO_TILE);
             kq[q] = widx - c;
-        }
-        if (c == 0) for (int q = 0; q < 6; ++q) k0[q] = kq[q];
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 6; ++q) ok = ok && kq[q] == k0[q];
-        all_ok = __syncthreads_and(ok ? 1 : 0);
-        d.affine = all_ok;
-        for (int q = 0; q < 6; ++q) d.aff_k[q] = (int16_t)(all_ok ? k0[q] : 0);
-    }
-    // ---- one length per edge (kind 3): slot q's length of vertex v is dist3[3 v + D_q] ----
-    //   forward slot (neighbour index > v): own row, entry = rank among v's forward slots        D_q = entry
-    //   backward slot: the neighbour's row, entry = rank of v among ITS forward slots            D_q = 3 (n - v) + entry
-    // The tile qualifies when it is affine, D_q is the same for all 256 vertices and nobody has more
-    // than 3 forward neighbours (rows with more -- mesh skeleton, shard seams -- keep only their first 3
-    // lengths in dist3 and must never be referenced).
-    {
-        __shared__ int j0[6];
-        int jq[6];
-        bool ok3 = all_ok != 0;
-        int fcnt = 0;
-        if (ok3) {                          // (36 scattered reads per vertex, affine tiles only)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int64_t n = nb[q];
-                if (n > v) { jq[q] = fcnt; ++fcnt; }
-                else {
-                    int fn = 0, idx = -1;
-                    for (int t = 0; t < 6; ++t) {
-                        const int32_t m = adj[n * 6 + t];
-                        if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
-                    }
-                    if (fn > 3 || idx < 0) ok3 = false;
-                    jq[q] = (int)(n - v) * 3 + (idx < 0 ? 0 : idx);
+            if (n > v) { jq[q] = fcnt; ++fcnt; }
+            else {                              // (6 scattered reads per backward slot, setup only)
+                int fn = 0, idx = -1;
+                for (int t = 0; t < 6; ++t) {
+                    const int32_t m = adj[n * 6 + t];
+                    if ((int64_t)m > n) { if ((int64_t)m == v) idx = fn; ++fn; }
                 }
+                if (fn > 3 || idx < 0) vd_ok = false;
+                jq[q] = (int)(n - v) * 3 + (idx < 0 ? 0 : idx);
             }
-            if (fcnt > 3) ok3 = false;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) jq[q] = 0;
         }
-        if (c == 0) for (int q = 0; q < 6; ++q) j0[q] = jq[q];
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 6; ++q) ok3 = ok3 && jq[q] == j0[q];
-        const int all3 = __syncthreads_and(ok3 ? 1 : 0);
-        d.d3 = all3 ? 1 : 0;
-        for (int q = 0; q < 4; ++q) d.d3_off[q] = all3 ? j0[q] : 0;
-        d.d3_off45[0] = all3 ? j0[4] : 0;
-        d.d3_off45[1] = all3 ? j0[5] : 0;
+        if (fcnt > 3) vd_ok = false;
     }
+    if (c == 0) for (int q = 0; q < 6; ++q) { k0[q] = kq[q]; j0[q] = jq[q]; }
+    if (c == ERO_TILE - 1) for (int q = 0; q < 6; ++q) { k1[q] = kq[q]; j1[q] = jq[q]; }
+    __syncthreads();
+    bool same_k0 = vk_ok, same_j0 = vk_ok && vd_ok, same_1 = vk_ok && vd_ok;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        same_k0 = same_k0 && kq[q] == k0[q];
+        same_j0 = same_j0 && kq[q] == k0[q] && jq[q] == j0[q];
+        same_1 = same_1 && kq[q] == k1[q] && jq[q] == j1[q];
+    }
+    const int all_ok = __syncthreads_and(same_k0 ? 1 : 0);
+    const int all3 = __syncthreads_and(same_j0 ? 1 : 0);
+    // two-piece: first vertex that does not follow vertex 0's constants, then ERO_EXC exceptions, then vertex 255's
+    const int BIGC = 1 << 20;
+    const int m0 = block_reduce_min(same_j0 ? BIGC : c, scratch);
+    const int tail_ok = __syncthreads_and((c < m0 + ERO_EXC || same_1) ? 1 : 0);
+    const int two = (tile_ok && !all3 && m0 >= 1 && m0 <= ERO_TILE - ERO_EXC - 1 && tail_ok) ? 1 : 0;
+    d.affine = all_ok;
+    d.d3 = all3 ? 1 : 0;
+    d.two = two;
+    d.split = two ? m0 : 0;
+    for (int q = 0; q < 6; ++q) {
+        d.aff_k[q] = (int16_t)((all_ok || two) ? k0[q] : 0);
+        d.aff_kB[q] = (int16_t)(two ? k1[q] : 0);
+        d.d3_offB[q] = two ? j1[q] : 0;
+    }
+    for (int q = 0; q < 4; ++q) d.d3_off[q] = (all3 || two) ? j0[q] : 0;
+    d.d3_off45[0] = (all3 || two) ? j0[4] : 0;
+    d.d3_off45[1] = (all3 || two) ? j0[5] : 0;
 #pragma unroll
     for (int q = 0; q < 6; ++q) adj16[v * 6 + q] = (uint16_t)code[q];          // adj16 is allocated in whole tiles
     if (c == 0) {
@@ -710,6 +787,7 @@ ero_plan_kernel(const int32_t *__restrict__ adj, int64_t n_own, int64_t capacity
         atomicMax(stats + 1, d.halo_used);
         if (d.affine) atomicAdd(stats + 2, 1);
         if (d.d3 & 1) atomicAdd(stats + 3, 1);
+        if (d.two) atomicAdd(stats + 4, 1);
     }
 }
 
@@ -770,15 +848,15 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
     EroTileDesc *desc = (EroTileDesc *)plan_mem;
     uint16_t *adj16 = (uint16_t *)((char *)plan_mem + n_tiles * sizeof(EroTileDesc));
     int32_t *stats = nullptr;
-    NXB_CUDA(cudaMalloc(&stats, 16));
-    NXB_CUDA(cudaMemsetAsync(stats, 0, 16, st));
+    NXB_CUDA(cudaMalloc(&stats, 32));
+    NXB_CUDA(cudaMemsetAsync(stats, 0, 32, st));
     ero_plan_kernel<<<(unsigned)n_tiles, ERO_TILE, 0, st>>>(adj, n_own, capacity, desc, adj16, stats);
     NXB_LAUNCH_CHECK();
-    int32_t h[4] = {0, 0, 0, 0};
-    NXB_CUDA(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, st));
+    int32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    NXB_CUDA(cudaMemcpyAsync(h, stats, 32, cudaMemcpyDeviceToHost, st));
     NXB_CUDA(cudaStreamSynchronize(st));
     NXB_CUDA(cudaFree(stats));
-    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; stats_host[3] = h[2]; stats_host[4] = h[3]; }
+    if (stats_host) { stats_host[0] = (int32_t)n_tiles; stats_host[1] = h[0]; stats_host[2] = h[1]; stats_host[3] = h[2]; stats_host[4] = h[3]; stats_host[5] = h[4]; }
     return NXB_OK;
 }
 
@@ -786,7 +864,7 @@ NXB_API int nxb_erode_plan_build(const int32_t *adj, int64_t n_own, int64_t capa
 // Launch side.  The configuration (pipeline depth, grid, environment switches) is resolved once
 // per call, the sweep loop runs here, not in Python.
 struct EroLaunchCfg {
-    int stages, use_affine, use_dist3, pdl, wait_in_sweep;
+    int stages, use_affine, use_dist3, use_two, pdl, wait_in_sweep, wait_hint_ns;
     size_t smem;
     int grid[2];                // [COMM]
 };
@@ -805,6 +883,8 @@ static int ero_launch_cfg(int64_t n_own, EroLaunchCfg &cfg)
     if (cfg.stages < 2 || cfg.stages > ERO_STAGES_MAX) cfg.stages = 3;
     cfg.use_affine = env_int("NXB_ERO_AFFINE", 1);          // read per call: tests toggle it
     cfg.use_dist3 = env_int("NXB_ERO_DIST3", 1);
+    cfg.wait_hint_ns = env_int("NXB_ERO_WAIT_HINT", 0);
+    cfg.use_two = env_int("NXB_ERO_TWO", 1);                // two-piece tiles (kind 4); 0: they run as kind 1
     cfg.pdl = env_int("NXB_ERO_PDL", 1);
     cfg.wait_in_sweep = env_int("NXB_ERO_WAIT_IN_SWEEP", 1);        // 0: separate one-warp wait kernel in front of every sweep
     cfg.smem = sizeof(EroStage) * cfg.stages;
@@ -856,7 +936,7 @@ static int ero_base_args(EroPlanArgs &a, const EroLaunchCfg &cfg, const void *pl
     a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
     a.adj = adj; a.dist = dist; a.dist3 = cfg.use_dist3 ? dist3 : nullptr;
     a.n_own = n_own; a.rain = rain;
-    a.n_stages = cfg.stages; a.use_affine = cfg.use_affine;
+    a.n_stages = cfg.stages; a.use_affine = cfg.use_affine; a.use_two = cfg.use_two; a.wait_hint_ns = cfg.wait_hint_ns;
     return NXB_OK;
 }
 

@@ -35,6 +35,14 @@
 //       sediment, bypass the bulk-copy engine (see nxb_erosion.cu: that engine, not HBM, is what
 //       the staged bytes queue on).  36 B / vertex-sweep from HBM; the rows of the previous mesh
 //       row were just streamed by another tile and come from L2.
+//   ERO_KIND_TWO      TWO-PIECE kind 3.  A tile that contains the end of a mesh row is not affine: the
+//       vertices of the next row see their neighbours at distances that differ by one, and the two
+//       row-end vertices (plus the vertex behind them, whose backward edge is stored in a shorter row)
+//       neighbour the mesh skeleton.  Such a tile -- 20 % of all tiles at d = 2500, all of the former
+//       kind-1 tiles -- is kind 3 with TWO sets of constants (K_q, D_q for c < split and for
+//       c >= split + ERO_EXC) and ERO_EXC exception vertices [split, split + ERO_EXC) that go through
+//       their explicit 16-bit codes and full length rows like a kind-1 vertex: 36 B / vertex-sweep
+//       instead of 60 for all but four vertices of the tile.
 #pragma once
 #include <stdint.h>
 
@@ -51,8 +59,10 @@
 #define ERO_KIND_CODES 1
 #define ERO_KIND_AFFINE 2
 #define ERO_KIND_AFFINE3 3
+#define ERO_KIND_TWO 4
+#define ERO_EXC 4               // kind 4: vertices [split, split + ERO_EXC) of the tile are handled through their explicit codes
 
-struct EroTileDesc {            // 128 bytes
+struct EroTileDesc {            // 256 bytes
     int32_t seg_start[ERO_NSEG];
     uint16_t seg_len[ERO_NSEG];
     uint16_t seg_off[ERO_NSEG]; // offset of the segment inside the halo area
@@ -65,9 +75,15 @@ struct EroTileDesc {            // 128 bytes
     int32_t d3_off[4];          // kind 3: D_q = float index of slot q's length in dist3 minus 3 v, q = 0..3
     int32_t send0, send1;       // multi-GPU shard: this tile's range of the send-entry list (filled by the driver)
     int32_t d3_off45[2];        // D_4, D_5
+    // ---- second half: kind 4 (two-piece) only
+    int32_t two;                // 1: tile qualifies for kind 4; aff_k / d3_off describe piece A (c < split)
+    int32_t split;              // first exception vertex
+    int16_t aff_kB[6];          // piece B (c >= split + ERO_EXC)
+    int32_t d3_offB[6];
+    int32_t pad[21];
 };
-static_assert(sizeof(EroTileDesc) == 128, "EroTileDesc layout");
-#define ERO_DESC_WORDS 32
+static_assert(sizeof(EroTileDesc) == 256, "EroTileDesc layout");
+#define ERO_DESC_WORDS 64
 // word indices of the descriptor fields (the producer warp holds one word per lane)
 #define ERO_DW_LEN (ERO_NSEG)
 #define ERO_DW_OFF (ERO_NSEG + ERO_NSEG / 2)
@@ -80,3 +96,7 @@ static_assert(sizeof(EroTileDesc) == 128, "EroTileDesc layout");
 #define ERO_DW_D3OFF (2 * ERO_NSEG + 8)     // 4 words (D_0..D_3); D_4, D_5 at ERO_DW_D3OFF45
 #define ERO_DW_D3OFF45 (2 * ERO_NSEG + 14)
 #define ERO_DW_SEND (2 * ERO_NSEG + 12)     // 2 words
+#define ERO_DW_TWO 32
+#define ERO_DW_SPLIT 33
+#define ERO_DW_AFFKB 34                     // 3 words
+#define ERO_DW_D3OFFB 37                    // 6 words

@@ -278,7 +278,7 @@ def adj_sort(adj):
 
 
 ERO_TILE = 256
-ERO_DESC_BYTES, ERO_DESC_WORDS = 128, 32
+ERO_DESC_BYTES, ERO_DESC_WORDS = 256, 64
 ERO_DW_SEND = 28           # csrc/nxb_erosion_plan.cuh: word index of (send0, send1) in a tile descriptor
 
 
@@ -314,11 +314,11 @@ class ErosionPlan:
         self.mem = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=adj.device)
         stats = (C.c_int32 * 8)()
         _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
-        self.n_tiles, self.n_irregular, self.max_halo, self.n_affine, self.n_affine3 = (stats[i] for i in range(5))
+        self.n_tiles, self.n_irregular, self.max_halo, self.n_affine, self.n_affine3, self.n_two = (stats[i] for i in range(6))
         self._dist3 = {}
 
     def descriptors(self):
-        """int32 [n_tiles, 32] view of the tile descriptors (nxb_erosion_plan.cuh EroTileDesc)."""
+        """int32 [n_tiles, 64] view of the tile descriptors (nxb_erosion_plan.cuh EroTileDesc)."""
         return self.mem[: self.n_tiles * ERO_DESC_BYTES].view(torch.int32).view(self.n_tiles, ERO_DESC_WORDS)
 
     def dist3_for(self, dist):

@@ -479,6 +479,31 @@ def test_erosion_implicit_adjacency_bit_identical(nx, monkeypatch, k):
     assert k < 700 or plan.n_affine > 0.15 * plan.n_tiles
 
 
+@pytest.mark.parametrize("k", [40, 300, 700, 1000, 2500])
+def test_erosion_two_piece_tiles_bit_identical(nx, monkeypatch, k):
+    """A tile that contains the end of a mesh row is swept as two affine pieces plus four exception
+    vertices (kind 4: 36 B/vertex for all but the exceptions); the result is bit for bit the one of
+    the explicit-code path the same tiles take with NXB_ERO_TWO=0.  At d=2500 these are all of the
+    tiles that are neither affine nor irregular."""
+    torch = nx.torch
+    pipe = nx.pipeline.TerrainPipeline(k, seed=12345, n_octaves=8, radius=1.0)
+    pipe.build_mesh()
+    h, _, _ = pipe.heights()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NXB_ERO_TWO", mode)
+        st = pipe.erosion_state(h.clone())
+        st.run(7)
+        st.step()                       # a run of one sweep: first-sweep / last-sweep handling of the rain
+        out[mode] = (st.heights.clone(), st.water.clone(), st.sediment.clone())
+    for a, b in zip(out["1"], out["0"]):
+        assert torch.equal(a, b)
+    plan = pipe._plan
+    print(f"k={k}: {plan.n_two} two-piece, {plan.n_affine3} one-piece, {plan.n_irregular} irregular of {plan.n_tiles} tiles")
+    if k >= 1000:
+        assert plan.n_two + plan.n_affine3 + plan.n_irregular > 0.97 * plan.n_tiles
+
+
 def test_erosion_exchange_capable_kernel_matches_plain_on_one_gpu(nx):
     """The COMM instantiation of the sweep kernel (the one every multi-GPU rank runs), driven on one
     GPU with no peers through the C-side loop, gives bit for bit what the single-GPU instantiation

@@ -16,11 +16,11 @@ pipe.build_mesh()
 h, _, _ = pipe.heights()
 st = pipe.erosion_state(h)
 p = st.plan
-print(f"d={k}: V={pipe.V} tiles {p.n_tiles} irregular {p.n_irregular} affine {p.n_affine} one-length-per-edge {p.n_affine3}", flush=True)
+print(f"d={k}: V={pipe.V} tiles {p.n_tiles} irregular {p.n_irregular} affine {p.n_affine} one-length-per-edge {p.n_affine3} two-piece {p.n_two}", flush=True)
 ref = None
-for env in ({}, {"NXB_ERO_STAGES": "2"}, {"NXB_ERO_STAGES": "4"}, {"NXB_ERO_STAGES": "6"},
-            {"NXB_ERO_DIST3": "0"}, {"NXB_ERO_PDL": "0"}, {"NXB_ERO_AFFINE": "0"}, {}):
-    for key in ("NXB_ERO_DIST3", "NXB_ERO_PDL", "NXB_ERO_AFFINE", "NXB_ERO_STAGES"):
+for env in ({}, {"NXB_ERO_WAIT_HINT": "500"}, {"NXB_ERO_WAIT_HINT": "2000"}, {"NXB_ERO_WAIT_HINT": "20000"}, {"NXB_ERO_WAIT_HINT": "2000", "NXB_ERO_STAGES": "4"}, {"NXB_ERO_STAGES": "4"},
+            {"NXB_ERO_TWO": "0"}, {"NXB_ERO_DIST3": "0"}, {"NXB_ERO_PDL": "0"}, {"NXB_ERO_AFFINE": "0"}, {}):
+    for key in ("NXB_ERO_DIST3", "NXB_ERO_PDL", "NXB_ERO_AFFINE", "NXB_ERO_STAGES", "NXB_ERO_TWO", "NXB_ERO_WAIT_HINT"):
         os.environ.pop(key, None)
     os.environ.update(env)
     best = 1e9
