@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnixis_b200.so")
+SO_PATH = os.environ.get("NXB_SO") or os.path.join(_HERE, "libnixis_b200.so")     # NXB_SO: A/B runs of kernel variants (tools/ab_probe.py)
 
 _p = C.c_void_p
 _i64 = C.c_int64

@@ -500,7 +500,7 @@ def test_erosion_two_piece_tiles_bit_identical(nx, monkeypatch, k):
         assert torch.equal(a, b)
     plan = pipe._plan
     print(f"k={k}: {plan.n_two} two-piece, {plan.n_affine3} one-piece, {plan.n_irregular} irregular of {plan.n_tiles} tiles")
-    if k >= 1000:
+    if k >= 2500:
         assert plan.n_two + plan.n_affine3 + plan.n_irregular > 0.97 * plan.n_tiles
 
 
