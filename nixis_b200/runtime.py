@@ -315,11 +315,13 @@ class ErosionPlan:
         stats = (C.c_int32 * 8)()
         _lib.call("nxb_erode_plan_build", _ptr(adj), self.n_own, self.capacity, _ptr(self.mem), stats, _stream())
         self.n_tiles, self.n_irregular, self.max_halo, self.n_affine, self.n_affine3, self.n_two = (stats[i] for i in range(6))
+        # descriptor size as the LIBRARY lays it out (plan = descriptors, then 16-bit codes of whole tiles)
+        self.desc_bytes = (nbytes // self.n_tiles - ERO_TILE * 6 * 2) if self.n_tiles else ERO_DESC_BYTES
         self._dist3 = {}
 
     def descriptors(self):
         """int32 [n_tiles, 64] view of the tile descriptors (nxb_erosion_plan.cuh EroTileDesc)."""
-        return self.mem[: self.n_tiles * ERO_DESC_BYTES].view(torch.int32).view(self.n_tiles, ERO_DESC_WORDS)
+        return self.mem[: self.n_tiles * self.desc_bytes].view(torch.int32).view(self.n_tiles, self.desc_bytes // 4)
 
     def dist3_for(self, dist):
         """One-length-per-edge table derived from the full [n,6] table `dist` (built once per table,
