@@ -393,6 +393,24 @@ def test_erosion1_vs_reference_golden(nx, golden, k, seed, R):
     assert r is h and relerr(h, g[f"{t}_it1_n100"]) <= 1e-5
 
 
+def test_erosion1_thousand_sweeps_vs_oracle(nx, oracle):
+    """erosion_iteration1 is the numerically stable variant -- a 1000-sweep trajectory
+    stays within 1e-5 of the range of the float64 reference arithmetic (assembled heights, -4000 .. 8850)."""
+    k = 64
+    pts, cells = icosphere.icosa_sphere(k)
+    adj = oracle.build_adjacency(cells)
+    oracle.sort_adjacency(adj)
+    perm, pgi = oracle.init(12345)
+    h0, _, _ = oracle.height_assembly(oracle.sample_octaves(pts, None, perm, pgi, 8, 1.5, 0.4, 2.5, 0.5, 1.0))
+    ref = h0.copy()
+    oracle.erode_terrain1(pts, adj, ref, 1000)
+    h = h0.copy()
+    r = nx.erosion.erode_terrain1(pts, adj, h, num_iter=1000, verbose=False)
+    err = np.abs(h - ref).max() / (ref.max() - ref.min())
+    print(f"erode_terrain1 x1000 at k={k}: max err / range = {err:.2e}")
+    assert r is h and err <= 1e-5
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 8, 32, 200])
 def test_adjacency_rows_of_a_vertex_range_match_the_whole_table(nx, k):
     """nxb_mesh_icosa_adj_rows (rows of a vertex range straight from the closed-form triangle generator,
