@@ -249,7 +249,7 @@ def workload_config(args):
     return {"workload": f"icosphere d={args.division} ({10 * args.division ** 2 + 2} verts), {args.octaves}-octave "
                         f"{'4-D ' if args.noise_dim == 4 else ''}OpenSimplex fBm + height assembly + {args.iters} erosion_iteration3 sweeps, seed {args.seed}, R=1",
             "division": args.division, "octaves": args.octaves, "erosion_iters": args.iters, "noise_dim": args.noise_dim,
-            "l2": "inputs larger than L2: every sweep streams 3.2 GB (h/w/s in+out 1.5 GB, edge lengths 1.5 GB, 16-bit adjacency of the non-affine tiles 0.15 GB) vs 126 MB of L2; no flush needed",
+            "l2": "inputs larger than L2: every sweep streams 2.35 GB at d=2500 (h/w/s in+out 1.5 GB, one stored length per edge 0.75 GB, descriptors and the few explicit-code tiles 0.1 GB) vs 126 MB of L2; no flush needed",
             "parallelism": f"vertex-range shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
 
 
@@ -427,8 +427,10 @@ def run_ours(args):
                 "tiles": {"total": plan.n_tiles, "irregular": plan.n_irregular, "affine": plan.n_affine,
                           "affine_one_length_per_edge": plan.n_affine3, "two_piece": plan.n_two},
                 "note": "achieved keeps SURVEY 8d's 60 B per vertex-iteration as numerator; the kernel itself moves "
-                        "less (36 B on affine tiles with one stored length per edge, 48 B on other affine tiles: see "
-                        "traffic), so frac may exceed 1"}
+                        "less (36 B per vertex on the 98 % affine / two-piece tiles with one stored length per edge: see "
+                        "traffic), so frac exceeds 1; real HBM traffic / avg_launch_ms is the honest bandwidth figure",
+                "achieved_real_gbs": (traffic / (ero_launch_ms * 1e-3) / 1e9) if traffic else None,
+                "frac_real": (traffic / (ero_launch_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None}
     fbm_obj = {"value": V * n_oct / (fbm_ms * 1e-3) / 1e6, "unit": "Mvert*octaves/s", "ms": fbm_ms,
                "roofline": {"kernel": "fbm3_fast_kernel" if args.noise_dim == 3 else "fbm_kernel<4>", "bound": "fp32", "achieved": fbm_tflops, "peak": fp32_peak,
                             "unit": "TFLOP/s", "frac": fbm_tflops / fp32_peak,
