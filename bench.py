@@ -436,7 +436,9 @@ def run_ours(args):
                             "unit": "TFLOP/s", "frac": fbm_tflops / fp32_peak,
                             "peak_source": "measured here: nxb_ffma_peak FFMA microbenchmark",
                             "algorithmic_flop_per_vert_octave": flop_per,
-                            "note": "lattice cell + candidate selection run in float64 (the reference's own decisions) on the FP64 pipe"}}
+                            "note": ("lattice cell + candidate selection run in float64 (the reference's own decisions) on the FP64 pipe"
+                                     if args.noise_dim == 3 else
+                                     "generic 4-D kernel (branches on the lattice region like the reference, FP32 throughout); no fast path yet")}}
     ero_obj = {"value": V * iters / (ero_ms * 1e-3) / 1e6, "unit": "Mvert-iters/s", "ms": ero_ms,
                "nonfinite_heights_after_last_step": nonfinite,
                "finite_data": {"sweeps": 100, "ms_per_sweep": min(fin_ms), "value": V / (min(fin_ms) * 1e-3) / 1e6,
