@@ -1,10 +1,12 @@
 // Erosion sweeps -- erosion.py:34-40, 76-99, 197-279 -- as a shared-memory-staged stencil.
 //
-// Bound by HBM and by consumer instruction issue at the same time (profiles/r01_ncu_*, r02_*).
+// No single unit is saturated (v11 at d=2500: HBM 78 % of the measured copy peak, issue slots 66 %, L2 40 %); the sweep
+// is bound by latency times concurrency -- see DESIGN.md section 4.2 for the five variants that established it.
 // Algorithmic traffic per vertex-iteration of erosion_iteration3:
 //   own h,w,s read 12 B + write 12 B + adjacency row 24 B + own position 12 B = 60 B.
 // What this implementation streams from HBM per vertex-iteration (nxb_erosion_plan.cuh):
 //   kind 3 (affine tile, one length per edge)  h,w,s read 12 + write 12 + dist3 12       = 36 B
+//   kind 4 (two affine pieces + 4 exceptions)  as kind 3 but for the exception vertices   = 36 B
 //   kind 2 (affine tile, full length rows)     ... + 6 edge lengths 24                   = 48 B
 //   kind 1 (explicit codes)                    ... + 24 + 16-bit tile-local adjacency 12 = 60 B
 //
@@ -41,9 +43,16 @@
 //     follows the bytes queued on the per-SM bulk-copy (TMA) engine, ~21 B/clk/SM, whatever their
 //     source.  So only what NEIGHBOURS share is staged (the {h, w} window and runs); the vertex's own
 //     sediment, its six edge lengths (kind 3: dist3[3 v + D_q]; kinds 1 / 2: its row of the full table)
-//     and, on kind-1 tiles, its 16-bit neighbour codes are plain coalesced loads issued before the
-//     barrier wait, which hides their latency: 6.3 KB per tile through the engine instead of 13.7 KB,
-//     and a pipeline stage shrinks from 18 KB to 7.3 KB.
+//     and, on kind-1 tiles, its 16-bit neighbour codes are plain coalesced loads: 6.3 KB per tile through
+//     the engine instead of 13.7 KB, and a pipeline stage shrinks from 18 KB to 7.4 KB.
+//   * v9 / v10 THOSE LOADS RUN ONE TILE AHEAD: the producer puts the next tile's descriptor words into the
+//     stage header and every consumer issues the next tile's loads behind the math of the current one, into
+//     the registers it reads an iteration later (one prefetch scoreboard: see the comments at the loads);
+//     32-bit indices, water stored already rained, slopes taken inside the tile-kind branches:
+//     0.545-0.576 -> 0.458-0.475 ms per sweep at d=2500.
+//   * v11 TWO-PIECE TILES (kind 4): a tile with the end of a mesh row inside is swept as kind 3 with two sets
+//     of constants and four exception vertices: 98 % of the tiles read no adjacency and one length per edge,
+//     2.62 -> 2.35 GB per sweep, same time.
 //   * ping-pong buffers replace the reference's three np.copy + copy-back pass (erosion.py:199-201,
 //     274-277); `water += rain` (erosion.py:182-183) is fused into the reads.
 //   * the sweep LOOP lives here (nxb_erode3_run_*): n sweeps are n launches issued from C with
