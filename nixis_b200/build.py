@@ -14,7 +14,7 @@ SOURCES = ["nxb_api.cu", "nxb_noise.cu", "nxb_mesh.cu", "nxb_adjacency.cu", "nxb
 # per-file extra flags: the reference-exact FP64 kernels must not contract a*b+c into FMA
 EXTRA_FLAGS = {"nxb_noise_f64.cu": ["-fmad=false"], "nxb_climate.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "-DNXB_HAVE_NOISE4"] + (["-DNXB_ERO_DEBUG_WAIT"] if os.environ.get("NXB_ERO_DEBUG_WAIT") else [])
+              "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "-DNXB_HAVE_NOISE4"] + (["-DNXB_ERO_PROFILE"] if os.environ.get("NXB_ERO_PROFILE") else [])
 
 
 def _nvcc():

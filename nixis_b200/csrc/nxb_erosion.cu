@@ -131,6 +131,7 @@ struct EroPlanArgs {
     int use_affine;                                     // honour the plan's affine tiles (implicit adjacency)
     int use_two;                                        // honour the plan's two-piece tiles (kind 4; needs dist3)
     int wait_hint_ns;                                   // consumers' barrier wait: suspend-time hint (0: plain poll loop)
+    unsigned long long *prof;                           // NXB_ERO_PROFILE builds: per-CTA cycle counters [grid][8] (else null)
     int n_stages;                                       // pipeline depth (<= ERO_STAGES_MAX)
     const float2 *hw_in;                                // {height, water} interleaved: ONE bulk copy per run
     const float *s_in;
@@ -327,6 +328,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         // ---------------- producer warp: lane 0 = own streams, lanes 1..ERO_NSEG = halo segments
         int s = 0;
         uint32_t ph_empty = 1;                  // parity the empty barrier of stage s must have passed
+#ifdef NXB_ERO_PROFILE
+        long long pt_decode = 0, pt_wait = 0, pt_hdr = 0, pt_issue = 0, pt0 = clock64(), pt_begin = pt0;
+#endif
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             const size_t v0 = (size_t)tile * ERO_TILE;
@@ -382,7 +386,13 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                     send_info = n | (int)(__reduce_or_sync(0xffffffffu, wbit) << 16);
                 }
             }
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); pt_decode += t - pt0; pt0 = t; }
+#endif
             nxb_mbar_wait(&empty[s], ph_empty);
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); pt_wait += t - pt0; pt0 = t; }
+#endif
             EroStage &st = stage[s];
             // lanes holding D_q of the next tile turn it into the dist3 index of that tile's vertex 0
             if (lane >= ERO_DW_D3OFF) st.nd[lane - ERO_DW_D3OFF] = (uint32_t)nxt + (tile + gridDim.x) * (3u * ERO_TILE);
@@ -401,6 +411,9 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                 st.split = split; st.nsplit = split_n;
             }
             __syncwarp();                       // the whole header is written before lane 0 arms the barrier
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); pt_hdr += t - pt0; pt0 = t; }
+#endif
             if (kind != ERO_KIND_CODES) {
                 // window layout: [v0 - 4, v0 + 260) of {h, w}, halo runs behind it; no adjacency codes
                 if (lane == 0) {
@@ -419,7 +432,17 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
             __syncwarp();
             ent = ent_n;
             if (++s == n_stages) { s = 0; ph_empty ^= 1u; }
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); pt_issue += t - pt0; pt0 = t; }
+#endif
         }
+#ifdef NXB_ERO_PROFILE
+        if (a.prof && lane == 0) {
+            unsigned long long *o = a.prof + (size_t)blockIdx.x * 8;
+            o[0] = (unsigned long long)pt_decode; o[1] = (unsigned long long)pt_wait; o[2] = (unsigned long long)pt_hdr;
+            o[3] = (unsigned long long)pt_issue; o[7] = (unsigned long long)(clock64() - pt_begin);
+        }
+#endif
     } else {
         // ---------------- consumer warps: thread c owns vertex v0 + c of every tile of this CTA
         const int c = tid - 32;
@@ -443,9 +466,18 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
         uint32_t v = blockIdx.x * (uint32_t)ERO_TILE + (uint32_t)c;
         const uint32_t v_step = gridDim.x * (uint32_t)ERO_TILE;
 
+#ifdef NXB_ERO_PROFILE
+        long long ct_wait = 0, ct_work = 0, ct0 = clock64(), ct_begin = ct0;
+#endif
         auto body = [&](EroPre &cur) {
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); ct_work += t - ct0; ct0 = t; }
+#endif
             if (a.wait_hint_ns) nxb_mbar_wait_hint(full_a, ph_full, (uint32_t)a.wait_hint_ns);
             else nxb_mbar_wait_a(full_a, ph_full);
+#ifdef NXB_ERO_PROFILE
+            { const long long t = clock64(); ct_wait += t - ct0; ct0 = t; }
+#endif
             const EroStage &st = *stp;
             const int kind = st.kind;
             // ---- multi-GPU: what this tile owes the peers.  A SPARSE tile (<= ERO_SEND_SCAN entries, a vertex
@@ -617,6 +649,12 @@ erode3_plan_kernel(const __grid_constant__ EroPlanArgs a)
                          :: "r"(x), "r"(nxb_smem_u32(&s_last)) : "memory");
         }
         for (uint32_t it = 0; it < my_tiles; ++it) body(pre);
+#ifdef NXB_ERO_PROFILE
+        if (a.prof && tid == 32) {
+            unsigned long long *o = a.prof + (size_t)blockIdx.x * 8;
+            o[4] = (unsigned long long)ct_wait; o[5] = (unsigned long long)ct_work; o[6] = my_tiles;
+        }
+#endif
     }
     if (COMM && a.comm.n_send_peers > 0) {
         // Every peer store of this CTA is visible system-wide before the CTA checks in: the consumers' stores
@@ -879,6 +917,16 @@ struct EroLaunchCfg {
 };
 
 static bool g_ero_attr_set[64] = {false};
+#ifdef NXB_ERO_PROFILE
+static unsigned long long *g_ero_prof = nullptr;       // [4096][8] cycle counters of the last sweep launched
+NXB_API int nxb_erode_profile_read(unsigned long long *host, int n_ctas)
+{
+    if (!g_ero_prof) return NXB_ERR_ARG;
+    NXB_CUDA(cudaDeviceSynchronize());
+    NXB_CUDA(cudaMemcpy(host, g_ero_prof, (size_t)n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return NXB_OK;
+}
+#endif
 
 static int env_int(const char *name, int dflt)
 {
@@ -945,6 +993,10 @@ static int ero_base_args(EroPlanArgs &a, const EroLaunchCfg &cfg, const void *pl
     a.adj16 = (const uint16_t *)((const char *)plan_mem + n_tiles * sizeof(EroTileDesc));
     a.adj = adj; a.dist = dist; a.dist3 = cfg.use_dist3 ? dist3 : nullptr;
     a.n_own = n_own; a.rain = rain;
+#ifdef NXB_ERO_PROFILE
+    if (!g_ero_prof) { NXB_CUDA(cudaMalloc(&g_ero_prof, 4096 * 8 * sizeof(unsigned long long))); NXB_CUDA(cudaMemset(g_ero_prof, 0, 4096 * 8 * sizeof(unsigned long long))); }
+    a.prof = g_ero_prof;
+#endif
     a.n_stages = cfg.stages; a.use_affine = cfg.use_affine; a.use_two = cfg.use_two; a.wait_hint_ns = cfg.wait_hint_ns;
     return NXB_OK;
 }
